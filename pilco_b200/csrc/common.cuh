@@ -1,0 +1,248 @@
+// common.cuh -- shared device helpers for the PILCO B200 engine (sm_100a).
+//
+// Small dense linear algebra on D<=16 matrices held in shared memory (one warp cooperates),
+// the table-driven fp64 exp used by the tile kernels, DMMA wrappers, TMA bulk-copy wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pilco_b200.h"
+
+#define PILCO_OK              0
+#define PILCO_ERR_NULL       -1
+#define PILCO_ERR_DIM        -2
+#define PILCO_ERR_WORKSPACE  -3
+#define PILCO_ERR_ALIGN      -4
+#define PILCO_ERR_LAUNCH     -5
+#define PILCO_ERR_UNSUPPORTED -6
+
+#define MAXD PILCO_MAX_D
+#define MAXE PILCO_MAX_E
+#define SLD  17                 // leading dimension of small smem matrices (odd -> conflict-light)
+#define NEG_PAD (-1.0e5)        // exponent value for padded rows/cols: exp() clamps it to ~1e-304
+
+#define CUDA_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return PILCO_ERR_LAUNCH; } while (0)
+
+static inline __host__ __device__ int pad64(int n) { return (n + 63) & ~63; }
+// row stride (in doubles) of zeta/U rows: multiple of 4 (DMMA k-step) and == 4 or 12 (mod 16) so
+// that the 8-column x 4-k B-fragment read is shared-memory bank-conflict free.
+static inline __host__ __device__ int ldz_of(int D) { return D <= 4 ? 4 : (D <= 12 ? 12 : 20); }
+static inline __host__ __device__ int ksteps_of(int D) { return (D + 3) / 4; }
+static inline __host__ __device__ int npairs_of(int E) { return E * (E + 1) / 2; }
+
+// unordered pair index q <-> (a,b), a<=b, b-major: q = b(b+1)/2 + a
+static inline __host__ __device__ void pair_decode(int q, int& a, int& b) {
+    int bb = 0;
+    while ((bb + 1) * (bb + 2) / 2 <= q) ++bb;
+    b = bb; a = q - bb * (bb + 1) / 2;
+}
+static inline __host__ __device__ int pair_index(int a, int b) { return a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b; }
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of `cnt` values per thread-private array `vals` -> result in smem out[0..cnt)
+// (valid for all threads after the trailing __syncthreads).  red must hold cnt*nwarps doubles.
+template <int MAXCNT>
+__device__ __forceinline__ void block_sum(double* vals, int cnt, double* red, double* out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int c = 0; c < cnt; ++c) {
+        double v = warp_sum(vals[c]);
+        if (lane == 0) red[c * nw + warp] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cnt; c += blockDim.x) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += red[c * nw + w];     // fixed order: deterministic
+        out[c] = v;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// small dense linear algebra, one warp, matrices in shared memory (row-major, leading dim SLD)
+// ---------------------------------------------------------------------------------------------
+// In-place lower Cholesky of the SPD matrix A[D][D] (only the lower triangle is referenced/written).
+// invd[j] = 1/L[j][j].  Returns false (to all lanes) if a pivot is not positive.
+__device__ __forceinline__ bool chol_warp(double* A, double* invd, int D, int lane) {
+    bool ok = true;
+    for (int j = 0; j < D; ++j) {
+        double d = A[j * SLD + j];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        const double piv = sqrt(d);
+        const double ip = 1.0 / piv;
+        __syncwarp();
+        if (lane == 0) { A[j * SLD + j] = piv; invd[j] = ip; }
+        for (int i = j + 1 + lane; i < D; i += 32) A[i * SLD + j] *= ip;
+        __syncwarp();
+        // trailing update: entries (i,k), j<k<=i<D, flattened over lanes
+        const int rem = D - j - 1;
+        const int cnt = rem * (rem + 1) / 2;
+        for (int e = lane; e < cnt; e += 32) {
+            int ii = 0;
+            while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+            const int kk = e - ii * (ii + 1) / 2;
+            const int i = j + 1 + ii, k = j + 1 + kk;
+            A[i * SLD + k] -= A[i * SLD + j] * A[k * SLD + j];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// Solve (L L^T) Y = B for ncols right-hand sides, B/Y in smem [D][SLD] (in place), lane per column.
+__device__ __forceinline__ void chol_solve_warp(const double* L, const double* invd, double* B,
+                                                int D, int ncols, int lane) {
+    for (int c = lane; c < ncols; c += 32) {
+        for (int i = 0; i < D; ++i) {                   // forward: L y = b
+            double v = B[i * SLD + c];
+            for (int k = 0; k < i; ++k) v -= L[i * SLD + k] * B[k * SLD + c];
+            B[i * SLD + c] = v * invd[i];
+        }
+        for (int i = D - 1; i >= 0; --i) {              // backward: L^T x = y
+            double v = B[i * SLD + c];
+            for (int k = i + 1; k < D; ++k) v -= L[k * SLD + i] * B[k * SLD + c];
+            B[i * SLD + c] = v * invd[i];
+        }
+    }
+    __syncwarp();
+}
+
+// log det of the factored matrix: 2 * sum log L_ii  (all lanes get the value)
+__device__ __forceinline__ double chol_logdet(const double* invd, int D) {
+    double acc = 0.0;
+    for (int j = 0; j < D; ++j) acc -= log(invd[j]);
+    return 2.0 * acc;
+}
+
+// LU with partial pivoting of A[D][D] in smem (in place), perm[D] row permutation, returns det
+// sign * prod(diag) through *det.  One warp.
+__device__ __forceinline__ void lu_warp(double* A, int* perm, int D, int lane, double* det) {
+    double dsign = 1.0;
+    for (int i = lane; i < D; i += 32) perm[i] = i;
+    __syncwarp();
+    for (int j = 0; j < D; ++j) {
+        // pivot search (all lanes redundantly; D<=16)
+        int p = j; double best = fabs(A[j * SLD + j]);
+        for (int i = j + 1; i < D; ++i) { double v = fabs(A[i * SLD + j]); if (v > best) { best = v; p = i; } }
+        __syncwarp();
+        if (p != j) {
+            for (int k = lane; k < D; k += 32) { double t = A[j * SLD + k]; A[j * SLD + k] = A[p * SLD + k]; A[p * SLD + k] = t; }
+            if (lane == 0) { int t = perm[j]; perm[j] = perm[p]; perm[p] = t; }
+            dsign = -dsign;
+        }
+        __syncwarp();
+        const double ip = 1.0 / A[j * SLD + j];
+        __syncwarp();
+        for (int i = j + 1 + lane; i < D; i += 32) A[i * SLD + j] *= ip;
+        __syncwarp();
+        const int rem = D - j - 1;
+        for (int e = lane; e < rem * rem; e += 32) {
+            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            A[i * SLD + k] -= A[i * SLD + j] * A[j * SLD + k];
+        }
+        __syncwarp();
+    }
+    double d = dsign;
+    for (int j = 0; j < D; ++j) d *= A[j * SLD + j];
+    *det = d;
+}
+
+// Solve A X = B given LU (perm applied to B rows first); B in smem [D][SLD] holds the UNPERMUTED rhs,
+// result written to Xo [D][SLD].  lane per column.
+__device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm, const double* B, double* Xo,
+                                              int D, int ncols, int lane) {
+    for (int c = lane; c < ncols; c += 32) {
+        for (int i = 0; i < D; ++i) {
+            double v = B[perm[i] * SLD + c];
+            for (int k = 0; k < i; ++k) v -= LU[i * SLD + k] * Xo[k * SLD + c];
+            Xo[i * SLD + c] = v;
+        }
+        for (int i = D - 1; i >= 0; --i) {
+            double v = Xo[i * SLD + c];
+            for (int k = i + 1; k < D; ++k) v -= LU[i * SLD + k] * Xo[k * SLD + c];
+            Xo[i * SLD + c] = v / LU[i * SLD + i];
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 exp for the tile kernels: x = (k*64 + j) ln2/64 + r,  exp(x) = 2^k * T[j] * (1 + expm1(r)).
+// |r| <= ln2/128 so a degree-5 expm1 polynomial is exact to < 1e-16 relative.  10 fp64-pipe
+// instructions + one shared-memory table read; arguments below -700 are clamped (result ~1e-304).
+// ---------------------------------------------------------------------------------------------
+#define EXP_TAB 64
+__device__ __forceinline__ void exp_table_init(double* tab) {
+    for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = exp2((double)j / (double)EXP_TAB);
+}
+
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+    // clamp very negative arguments with integer ops (keeps the fp64 pipe free)
+    {
+        const unsigned hi = (unsigned)__double2hiint(x);
+        if (hi > 0xC085E000u) x = -700.0;                 // x < -700 (or negative NaN)
+    }
+    const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
+    const double t  = fma(x, 92.33248261689366, MAGIC);   // x * 64/ln2, rounded to integer in the low bits
+    const int    ki = __double2loint(t);
+    const double kd = t - MAGIC;
+    double r = fma(kd, -0.010830424696249145, x);         // Cody-Waite: ln2/64 = C1 + C2
+    r = fma(kd, -3.623510646634843e-19, r);
+    double q = 0.008333333333333333;                      // expm1(r)/r, degree 4 in r
+    q = fma(q, r, 0.041666666666666664);
+    q = fma(q, r, 0.16666666666666666);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double tj = tab[ki & (EXP_TAB - 1)];
+    const double em1 = q * r;
+    const double v = fma(tj, em1, tj);                    // T[j] * exp(r), in [1, 2.02)
+    // scale by 2^k: add k to the exponent field (k >= -1011 after the clamp, v normal)
+    const int k = ki >> 6;
+    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA: D(8x8) = A(8x4) * B(4x8) + C, fp64 (legacy mma.sync path -- tcgen05 has no f64 kind).
+// lane = 4*g + t:  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy (1-D cp.async.bulk, SASS UBLKCP) global -> shared, completion on an mbarrier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// bytes must be a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,507 @@
+// factorize.cu -- GP factorisations on the device (fp64):
+//   pilco_gp_factorize    MGPR.calculate_factorizations   pilco/models/mgpr.py:81-89  (gp0.m:46-61)
+//   pilco_fitc_factorize  SMGPR.calculate_factorizations  pilco/models/smgpr.py:24-45 (gp1.m:52-82)
+// Building blocks: SE-ARD (cross-)Gram kernel, blocked right-looking Cholesky (one CTA per matrix),
+// blocked triangular inverse, a batched fp64 GEMM with transposes, blocked triangular solves for beta.
+// These run once per set_data / hyper-parameter change (dynamics GP) or once per loss evaluation
+// (RBF policy, bf<=128), never inside the H-step loop.
+#include "common.cuh"
+
+#define FB 32                     // factorisation block size
+
+// -------------------------------------------------------------------------------------------------
+// SE-ARD Gram:  K[i][j] = sf2 exp(-0.5 sum_d ((x1_i - x2_j)/ell_d)^2) + diag_add*(i==j)
+// grid (ceil(n2/32), ceil(n1/8), batch) block (32, 8).  Output leading dimension ldo; entries with
+// i>=n1 or j>=n2 inside [0,rows_out) x [0,cols_out) are written as 0 (1 on the diagonal if unit_pad).
+// -------------------------------------------------------------------------------------------------
+struct GramArgs {
+    int n1, n2, D, E;
+    const double* X1; long long X1_bs;       // [n1,D] per batch b
+    const double* X2; long long X2_bs;       // [n2,D]
+    const double* ell; long long ell_bs;     // [E,D]
+    const double* sf2; long long sf2_bs;     // [E]
+    const double* dadd; long long dadd_bs;   // [E] added on the diagonal (or NULL)
+    double dconst;                           // constant added on the diagonal
+    double* out; int ldo; long long out_ms;  // matrix stride (per (b,e))
+    int rows_out, cols_out, unit_pad;
+};
+
+__global__ void __launch_bounds__(256) gram_kernel(GramArgs g) {
+    const int z = blockIdx.z, bidx = z / g.E, e = z % g.E;
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.rows_out || j >= g.cols_out) return;
+    double* out = g.out + (size_t)z * g.out_ms;
+    double v;
+    if (i < g.n1 && j < g.n2) {
+        const double* x1 = g.X1 + (size_t)bidx * g.X1_bs + (size_t)i * g.D;
+        const double* x2 = g.X2 + (size_t)bidx * g.X2_bs + (size_t)j * g.D;
+        const double* ell = g.ell + (size_t)bidx * g.ell_bs + (size_t)e * g.D;
+        double d2 = 0.0;
+        for (int d = 0; d < g.D; ++d) { const double t = (x1[d] - x2[d]) / ell[d]; d2 = fma(t, t, d2); }
+        v = g.sf2[(size_t)bidx * g.sf2_bs + e] * exp(-0.5 * d2);
+        if (i == j) v += g.dconst + (g.dadd ? g.dadd[(size_t)bidx * g.dadd_bs + e] : 0.0);
+    } else {
+        v = (g.unit_pad && i == j) ? 1.0 : 0.0;
+    }
+    out[(size_t)i * g.ldo + j] = v;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky, in place, lower triangle, one CTA (256 threads) per matrix.
+// Only the lower triangle is meaningful on exit.  info[b] |= 2 if a pivot is not positive.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_kernel(int n, double* Aall, int ld, long long ms, int mats_per_b, int* info) {
+    __shared__ double sD[FB][FB + 1];
+    __shared__ double sPi[64][FB + 1];
+    __shared__ double sPj[64][FB + 1];
+    __shared__ int sfail;
+    double* A = Aall + (size_t)blockIdx.x * ms;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sfail = 0;
+    for (int k0 = 0; k0 < n; k0 += FB) {
+        const int kb = min(FB, n - k0);
+        __syncthreads();
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e / FB, j = e % FB;
+            sD[i][j] = (i < kb && j < kb) ? A[(size_t)(k0 + i) * ld + k0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // left-looking Cholesky of the diagonal block, lane = row
+            for (int j = 0; j < kb; ++j) {
+                double v = sD[lane][j];
+                for (int k = 0; k < j; ++k) v = fma(-sD[lane][k], sD[j][k], v);
+                double piv = __shfl_sync(0xffffffffu, v, j);
+                if (!(piv > 0.0)) { if (lane == 0) sfail = 1; piv = 1.0; }
+                const double rp = 1.0 / sqrt(piv);
+                __syncwarp();
+                if (lane >= j) sD[lane][j] = (lane == j) ? sqrt(piv) : v * rp;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kb * kb; e += 256) {          // write the factored block back
+            const int i = e / kb, j = e % kb;
+            A[(size_t)(k0 + i) * ld + k0 + j] = (j <= i) ? sD[i][j] : 0.0;
+        }
+        // panel: rows below the block, one thread per row:  x L_kk^T = a
+        for (int i = k0 + kb + tid; i < n; i += 256) {
+            double x[FB];
+            double* arow = A + (size_t)i * ld + k0;
+#pragma unroll
+            for (int j = 0; j < FB; ++j) x[j] = j < kb ? arow[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+                if (j < kb) {
+                    double v = x[j];
+#pragma unroll
+                    for (int k = 0; k < j; ++k) v = fma(-x[k], sD[j][k], v);
+                    x[j] = v / sD[j][j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < FB; ++j) if (j < kb) arow[j] = x[j];
+        }
+        __syncthreads();
+        // trailing update A[i][j] -= sum_k L[i][k0+k] L[j][k0+k], lower triangle, 64x64 tiles
+        const int t0 = k0 + kb;
+        if (t0 >= n) break;
+        const int ntile = (n - t0 + 63) / 64;
+        const int ty = tid / 16, tx = tid % 16;
+        for (int ti = 0; ti < ntile; ++ti) {
+            for (int tj = 0; tj <= ti; ++tj) {
+                __syncthreads();
+                for (int e = tid; e < 64 * FB; e += 256) {
+                    const int rr = e / FB, k = e % FB;
+                    const int gi = t0 + ti * 64 + rr, gj = t0 + tj * 64 + rr;
+                    sPi[rr][k] = (gi < n && k < kb) ? A[(size_t)gi * ld + k0 + k] : 0.0;
+                    sPj[rr][k] = (gj < n && k < kb) ? A[(size_t)gj * ld + k0 + k] : 0.0;
+                }
+                __syncthreads();
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                for (int k = 0; k < FB; ++k) {
+                    double pi[4], pj[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { pi[a] = sPi[ty + 16 * a][k]; pj[a] = sPj[tx + 16 * a][k]; }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(pi[a], pj[b], acc[a][b]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int gi = t0 + ti * 64 + ty + 16 * a, gj = t0 + tj * 64 + tx + 16 * b;
+                        if (gi < n && gj <= gi) A[(size_t)gi * ld + gj] -= acc[a][b];
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && sfail && info) atomicOr(&info[blockIdx.x / mats_per_b], 2);
+}
+
+// -------------------------------------------------------------------------------------------------
+// inverse of the FB x FB diagonal blocks of a lower-triangular L:  X[I][I] = L[I][I]^-1
+// grid (nblocks, batch), one warp; lane = column.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) tri_diag_inv_kernel(int n, const double* Lall, int ld, long long ms,
+                                                          double* Xall, int ldx, long long xs) {
+    __shared__ double sL[FB][FB + 1];
+    __shared__ double sX[FB][FB + 1];
+    const int I = blockIdx.x, lane = threadIdx.x;
+    const double* L = Lall + (size_t)blockIdx.y * ms;
+    double* X = Xall + (size_t)blockIdx.y * xs;
+    const int k0 = I * FB, kb = min(FB, n - k0);
+    for (int i = 0; i < FB; ++i)
+        sL[i][lane] = (i < kb && lane < kb) ? L[(size_t)(k0 + i) * ld + k0 + lane] : (i == lane ? 1.0 : 0.0);
+    __syncwarp();
+    const int c = lane;
+    for (int i = 0; i < FB; ++i) {
+        double v = (i == c) ? 1.0 : 0.0;
+        for (int k = c; k < i; ++k) v = fma(-sL[i][k], sX[k][c], v);
+        sX[i][c] = (i >= c) ? v / sL[i][i] : 0.0;
+    }
+    __syncwarp();
+    for (int i = 0; i < kb; ++i) if (lane < kb) X[(size_t)(k0 + i) * ldx + k0 + lane] = sX[i][lane];
+}
+
+// -------------------------------------------------------------------------------------------------
+// batched GEMM  C = alpha op(A) op(B) + beta C   (row-major; op = transpose if flag set)
+// grid (ceil(n/64), ceil(m/64), batch), 256 threads, 4x4 per thread, k-tile 16.
+// -------------------------------------------------------------------------------------------------
+struct GemmArgs {
+    int m, n, k; int ta, tb;
+    double alpha, beta;
+    const double* A; int lda; long long sa;
+    const double* B; int ldb; long long sb;
+    double* C; int ldc; long long sc;
+};
+
+__global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
+    __shared__ double sA[16][64 + 1];
+    __shared__ double sB[16][64 + 1];
+    const double* A = g.A + (size_t)blockIdx.z * g.sa;
+    const double* B = g.B + (size_t)blockIdx.z * g.sb;
+    double* C = g.C + (size_t)blockIdx.z * g.sc;
+    const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int k0 = 0; k0 < g.k; k0 += 16) {
+        for (int e = tid; e < 16 * 64; e += 256) {
+            int kk, ii;
+            if (g.ta) { ii = e % 64; kk = e / 64; } else { kk = e % 16; ii = e / 16; }
+            const int gi = i0 + ii, gk = k0 + kk;
+            double v = 0.0;
+            if (gi < g.m && gk < g.k) v = g.ta ? A[(size_t)gk * g.lda + gi] : A[(size_t)gi * g.lda + gk];
+            sA[kk][ii] = v;
+        }
+        for (int e = tid; e < 16 * 64; e += 256) {
+            int kk, jj;
+            if (g.tb) { kk = e % 16; jj = e / 16; } else { jj = e % 64; kk = e / 64; }
+            const int gj = j0 + jj, gk = k0 + kk;
+            double v = 0.0;
+            if (gj < g.n && gk < g.k) v = g.tb ? B[(size_t)gj * g.ldb + gk] : B[(size_t)gk * g.ldb + gj];
+            sB[kk][jj] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) { a[x] = sA[kk][ty + 16 * x]; b[x] = sB[kk][tx + 16 * x]; }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            const int gi = i0 + ty + 16 * x, gj = j0 + tx + 16 * y;
+            if (gi < g.m && gj < g.n) {
+                double* c = C + (size_t)gi * g.ldc + gj;
+                *c = g.alpha * acc[x][y] + (g.beta != 0.0 ? g.beta * (*c) : 0.0);
+            }
+        }
+}
+
+static int gemm(cudaStream_t st, int batch, int m, int n, int k, int ta, int tb, double alpha,
+                const double* A, int lda, long long sa, const double* B, int ldb, long long sb,
+                double beta, double* C, int ldc, long long sc) {
+    if (m <= 0 || n <= 0) return PILCO_OK;
+    GemmArgs g{m, n, k, ta, tb, alpha, beta, A, lda, sa, B, ldb, sb, C, ldc, sc};
+    dim3 grid((n + 63) / 64, (m + 63) / 64, batch);
+    gemm_kernel<<<grid, 256, 0, st>>>(g);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+// X = L^-1 (lower triangular), X zero-initialised by the caller outside the diagonal blocks.
+// T: scratch [batch, FB, ld]
+static int tri_inverse(cudaStream_t st, int batch, int n, const double* L, int ld, long long ms,
+                       double* X, int ldx, long long xs, double* T, long long ts) {
+    const int nb = (n + FB - 1) / FB;
+    tri_diag_inv_kernel<<<dim3(nb, batch), 32, 0, st>>>(n, L, ld, ms, X, ldx, xs);
+    CUDA_LAUNCH_CHECK();
+    for (int I = 1; I < nb; ++I) {
+        const int r0 = I * FB, rb = min(FB, n - r0);
+        // T = L[I, 0:r0] X[0:r0, 0:r0]
+        int rc = gemm(st, batch, rb, r0, r0, 0, 0, 1.0, L + (size_t)r0 * ld, ld, ms, X, ldx, xs, 0.0, T, ld, ts);
+        if (rc) return rc;
+        // X[I, 0:r0] = -X_II T
+        rc = gemm(st, batch, rb, r0, rb, 0, 0, -1.0, X + (size_t)r0 * ldx + r0, ldx, xs, T, ld, ts, 0.0,
+                  X + (size_t)r0 * ldx, ldx, xs);
+        if (rc) return rc;
+    }
+    return PILCO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// small helpers
+// -------------------------------------------------------------------------------------------------
+// y[z][i] = sum_j op(A[z])[i][j] x[z][j]   (one warp per row; grid (m, batch))
+__global__ void __launch_bounds__(32) matvec_kernel(int m, int k, int ta, const double* A, int lda, long long sa,
+                                                    const double* x, long long xs, int xinc,
+                                                    double* y, long long ys) {
+    const int i = blockIdx.x, z = blockIdx.y, lane = threadIdx.x;
+    const double* Az = A + (size_t)z * sa;
+    const double* xz = x + (size_t)z * xs;
+    double v = 0.0;
+    for (int j = lane; j < k; j += 32) v = fma(ta ? Az[(size_t)j * lda + i] : Az[(size_t)i * lda + j], xz[(size_t)j * xinc], v);
+    v = warp_sum(v);
+    if (lane == 0) y[(size_t)z * ys + i] = v;
+}
+
+// Solve L L^T x = y for one right-hand side per matrix by blocked substitution (one CTA per matrix).
+// L lower triangular [n,n] (ld), y stride yinc, x contiguous [n].
+// Matrix z = b*E + e takes its right-hand side from column e of Y_b ([n,E], batch stride Y_bs).
+__global__ void __launch_bounds__(256) chol_solve_vec_kernel(int n, const double* Lall, int ld, long long ms,
+                                                             int E, const double* Y, long long Y_bs,
+                                                             double* xall, long long xs) {
+    extern __shared__ double sx[];            // n doubles
+    __shared__ double sD[FB][FB + 1];
+    const double* L = Lall + (size_t)blockIdx.x * ms;
+    const double* y = Y + (size_t)(blockIdx.x / E) * Y_bs + (blockIdx.x % E);
+    const int yinc = E;
+    double* x = xall + (size_t)blockIdx.x * xs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < n; i += 256) sx[i] = y[(size_t)i * yinc];
+    __syncthreads();
+    const int nb = (n + FB - 1) / FB;
+    for (int I = 0; I < nb; ++I) {                                   // forward  L z = y
+        const int r0 = I * FB, rb = min(FB, n - r0);
+        for (int rr = warp; rr < rb; rr += 8) {                      // sx[r0+rr] -= L[r0+rr, 0:r0] . sx[0:r0]
+            double v = 0.0;
+            for (int k = lane; k < r0; k += 32) v = fma(L[(size_t)(r0 + rr) * ld + k], sx[k], v);
+            v = warp_sum(v);
+            if (lane == 0) sx[r0 + rr] -= v;
+        }
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e / FB, j = e % FB;
+            sD[i][j] = (i < rb && j < rb) ? L[(size_t)(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < rb; ++i) {
+                double v = sx[r0 + i];
+                for (int k = 0; k < i; ++k) v = fma(-sD[i][k], sx[r0 + k], v);
+                sx[r0 + i] = v / sD[i][i];
+            }
+        }
+        __syncthreads();
+    }
+    for (int I = nb - 1; I >= 0; --I) {                              // backward  L^T x = z
+        const int r0 = I * FB, rb = min(FB, n - r0);
+        for (int rr = warp; rr < rb; rr += 8) {                      // sx[r0+rr] -= L[r1:, r0+rr] . sx[r1:]
+            double v = 0.0;
+            for (int k = r0 + rb + lane; k < n; k += 32) v = fma(L[(size_t)k * ld + r0 + rr], sx[k], v);
+            v = warp_sum(v);
+            if (lane == 0) sx[r0 + rr] -= v;
+        }
+        for (int e = tid; e < FB * FB; e += 256) {
+            const int i = e / FB, j = e % FB;
+            sD[i][j] = (i < rb && j < rb) ? L[(size_t)(r0 + i) * ld + r0 + j] : (i == j ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = rb - 1; i >= 0; --i) {
+                double v = sx[r0 + i];
+                for (int k = i + 1; k < rb; ++k) v = fma(-sD[k][i], sx[r0 + k], v);
+                sx[r0 + i] = v / sD[i][i];
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) x[i] = sx[i];
+}
+
+__global__ void fill_kernel(double* p, size_t count, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+static void fill(cudaStream_t st, double* p, size_t count, double v) {
+    if (count == 0) return;
+    if (v == 0.0) { cudaMemsetAsync(p, 0, count * sizeof(double), st); return; }
+    fill_kernel<<<(unsigned)min((size_t)1024, (count + 255) / 256), 256, 0, st>>>(p, count, v);
+}
+
+// FITC: G[j] = sqrt(1 + (sf2 - sum_i V[i][j]^2)/sn2);  V[:,j] /= G[j];  Vg = V/G (second division)
+__global__ void fitc_scale_kernel(int Mi, int N, double* V, int ldv, long long vs, double* Vg, const double* sf2,
+                                  const double* sn2) {
+    const int e = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double* Ve = V + (size_t)e * vs;
+    double* Vge = Vg + (size_t)e * vs;
+    double ss = 0.0;
+    for (int i = 0; i < Mi; ++i) { const double v = Ve[(size_t)i * ldv + j]; ss = fma(v, v, ss); }
+    const double G = sqrt(1.0 + (sf2[e] - ss) / sn2[e]);
+    for (int i = 0; i < Mi; ++i) {
+        const double v = Ve[(size_t)i * ldv + j] / G;
+        Ve[(size_t)i * ldv + j] = v;
+        Vge[(size_t)i * ldv + j] = v / G;
+    }
+}
+
+__global__ void add_diag_kernel(int n, double* A, int ld, long long ms, const double* d) {
+    const int e = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)e * ms + (size_t)i * ld + i] += d[e];
+}
+
+__global__ void fitc_axpy_kernel(int n, double* C, int ldc, long long cs, const double* Tm, int ldt, long long ts, const double* a) {
+    const int e = blockIdx.z, j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i < n && j < n) C[(size_t)e * cs + (size_t)i * ldc + j] -= a[e] * Tm[(size_t)e * ts + (size_t)i * ldt + j];
+}
+
+extern "C" {
+
+size_t pilco_gp_factorize_workspace_bytes(int n, int E, int B) {
+    if (n < 1 || E < 1 || B < 1) return 0;
+    const size_t ldk = pad64(n);
+    return ((size_t)B * E * (2 * ldk * ldk + FB * ldk)) * sizeof(double);
+}
+
+int pilco_gp_factorize(int n, int D, int E, int B,
+                       const double* X, long long X_bs, const double* Y, long long Y_bs,
+                       const double* ell, long long ell_bs, const double* sf2, long long sf2_bs,
+                       const double* sn2, long long sn2_bs,
+                       double* iK, int ldk, double* beta, int* info,
+                       void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    if (!X || !Y || !ell || !sf2 || !sn2 || !beta || !ws) return PILCO_ERR_NULL;
+    if (n < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || B < 1) return PILCO_ERR_DIM;
+    if (iK && ldk < pad64(n)) return PILCO_ERR_DIM;
+    if (ws_bytes < pilco_gp_factorize_workspace_bytes(n, E, B)) return PILCO_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ldw = pad64(n);
+    const long long ms = (long long)ldw * ldw;
+    const int batch = B * E;
+    double* L = (double*)ws;
+    double* Xi = L + (size_t)batch * ms;
+    double* T = Xi + (size_t)batch * ms;
+    if (info) cudaMemsetAsync(info, 0, sizeof(int) * B, st);
+    // K + sn2 I  (mgpr.py:82-84), zero outside n x n
+    GramArgs g{n, n, D, E, X, X_bs, X, X_bs, ell, ell_bs, sf2, sf2_bs, sn2, sn2_bs, 0.0, L, ldw, ms, ldw, ldw, 0};
+    gram_kernel<<<dim3((ldw + 31) / 32, (ldw + 7) / 8, batch), dim3(32, 8), 0, st>>>(g);
+    CUDA_LAUNCH_CHECK();
+    chol_kernel<<<batch, 256, 0, st>>>(n, L, ldw, ms, E, info);
+    CUDA_LAUNCH_CHECK();
+    // beta = (L L^T)^-1 y_e   (mgpr.py:86-88)
+    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ldw, ms, E, Y, Y_bs, beta, n);
+    CUDA_LAUNCH_CHECK();
+    if (iK) {
+        // iK = L^-T L^-1 through the explicit triangular inverse (mgpr.py:85)
+        cudaMemsetAsync(Xi, 0, (size_t)batch * ms * sizeof(double), st);
+        int rc = tri_inverse(st, batch, n, L, ldw, ms, Xi, ldw, ms, T, (long long)FB * ldw);
+        if (rc) return rc;
+        cudaMemsetAsync(iK, 0, (size_t)batch * ldk * ldk * sizeof(double), st);
+        rc = gemm(st, batch, n, n, n, 1, 0, 1.0, Xi, ldw, ms, Xi, ldw, ms, 0.0, iK, ldk, (long long)ldk * ldk);
+        if (rc) return rc;
+    }
+    return PILCO_OK;
+}
+
+size_t pilco_fitc_workspace_bytes(int N, int Mi, int E) {
+    if (N < 1 || Mi < 1 || E < 1) return 0;
+    const size_t ldm = pad64(Mi) + 64, ldn = pad64(N);
+    // L, Linv, Am, Aminv, iAt, T : E*ldm*ldm each (6) ; Kmn/V, Vg : E*ldm*ldn each (2) ; w, w2 : E*ldm (2)
+    return (6 * E * ldm * ldm + 2 * E * ldm * ldn + 2 * E * ldm) * sizeof(double);
+}
+
+int pilco_fitc_factorize(int N, int Mi, int D, int E, const double* X, const double* Z, const double* Y,
+                         const double* ell, const double* sf2, const double* sn2,
+                         double* iK, int ldk, double* beta, int* info, void* ws, size_t ws_bytes,
+                         pilco_stream_t stream) {
+    if (!X || !Z || !Y || !ell || !sf2 || !sn2 || !iK || !beta || !ws) return PILCO_ERR_NULL;
+    if (N < 1 || Mi < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE) return PILCO_ERR_DIM;
+    if (ldk < pad64(Mi)) return PILCO_ERR_DIM;
+    if (ws_bytes < pilco_fitc_workspace_bytes(N, Mi, E)) return PILCO_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ldm = pad64(Mi) + 64, ldn = pad64(N);
+    const long long mm = (long long)ldm * ldm, mn = (long long)ldm * ldn;
+    double* w0 = (double*)ws;
+    double* L = w0;            double* Linv = L + E * mm;   double* Am = Linv + E * mm;
+    double* Aminv = Am + E * mm; double* iAt = Aminv + E * mm; double* T = iAt + E * mm;
+    double* V = T + E * mm;    double* Vg = V + E * mn;
+    double* w = Vg + E * mn;   double* w2 = w + (size_t)E * ldm;
+    if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+    cudaMemsetAsync(ws, 0, pilco_fitc_workspace_bytes(N, Mi, E), st);
+    // Kmm + 1e-6 I  (smgpr.py:27), Kmn (smgpr.py:28)
+    GramArgs gmm{Mi, Mi, D, E, Z, 0, Z, 0, ell, 0, sf2, 0, nullptr, 0, 1e-6, L, ldm, mm, ldm, ldm, 0};
+    gram_kernel<<<dim3((ldm + 31) / 32, (ldm + 7) / 8, E), dim3(32, 8), 0, st>>>(gmm);
+    CUDA_LAUNCH_CHECK();
+    GramArgs gmn{Mi, N, D, E, Z, 0, X, 0, ell, 0, sf2, 0, nullptr, 0, 0.0, Vg, ldn, mn, Mi, N, 0};
+    gram_kernel<<<dim3((N + 31) / 32, (Mi + 7) / 8, E), dim3(32, 8), 0, st>>>(gmn);     // Kmn -> Vg (temp)
+    CUDA_LAUNCH_CHECK();
+    chol_kernel<<<E, 256, 0, st>>>(Mi, L, ldm, mm, E, info);                            // L = chol(Kmm)  :29
+    CUDA_LAUNCH_CHECK();
+    int rc = tri_inverse(st, E, Mi, L, ldm, mm, Linv, ldm, mm, T, mm);                   // Linv = L^-1
+    if (rc) return rc;
+    rc = gemm(st, E, Mi, N, Mi, 0, 0, 1.0, Linv, ldm, mm, Vg, ldn, mn, 0.0, V, ldn, mn); // V = L^-1 Kmn  :30
+    if (rc) return rc;
+    fitc_scale_kernel<<<dim3((N + 127) / 128, E), 128, 0, st>>>(Mi, N, V, ldn, mn, Vg, sf2, sn2);   // :31-33
+    CUDA_LAUNCH_CHECK();
+    rc = gemm(st, E, Mi, Mi, N, 0, 1, 1.0, V, ldn, mn, V, ldn, mn, 0.0, Am, ldm, mm);    // V V^T
+    if (rc) return rc;
+    add_diag_kernel<<<dim3((Mi + 127) / 128, E), 128, 0, st>>>(Mi, Am, ldm, mm, sn2);    // + sn2 I   :34-35
+    CUDA_LAUNCH_CHECK();
+    chol_kernel<<<E, 256, 0, st>>>(Mi, Am, ldm, mm, E, info);                           // Am
+    CUDA_LAUNCH_CHECK();
+    fill(st, T, (size_t)E * mm, 0.0);
+    rc = tri_inverse(st, E, Mi, Am, ldm, mm, Aminv, ldm, mm, T, mm);                     // Am^-1
+    if (rc) return rc;
+    rc = gemm(st, E, Mi, Mi, Mi, 0, 0, 1.0, Aminv, ldm, mm, Linv, ldm, mm, 0.0, iAt, ldm, mm);   // iAt = (L Am)^-1  :36-37
+    if (rc) return rc;
+    // beta = L^-T Am^-T Am^-1 (V/G) y     (:38-42)
+    matvec_kernel<<<dim3(Mi, E), 32, 0, st>>>(Mi, N, 0, Vg, ldn, mn, Y, 1, E, w, ldm);   // w = Vg y_e  (y stride E, offset e)
+    CUDA_LAUNCH_CHECK();
+    matvec_kernel<<<dim3(Mi, E), 32, 0, st>>>(Mi, Mi, 0, Aminv, ldm, mm, w, ldm, 1, w2, ldm);
+    CUDA_LAUNCH_CHECK();
+    matvec_kernel<<<dim3(Mi, E), 32, 0, st>>>(Mi, Mi, 1, Aminv, ldm, mm, w2, ldm, 1, w, ldm);
+    CUDA_LAUNCH_CHECK();
+    matvec_kernel<<<dim3(Mi, E), 32, 0, st>>>(Mi, Mi, 1, Linv, ldm, mm, w, ldm, 1, beta, Mi);
+    CUDA_LAUNCH_CHECK();
+    // iK = Kmm^-1 - sn2 iAt^T iAt = Linv^T Linv - sn2 iAt^T iAt   (:43-44)
+    cudaMemsetAsync(iK, 0, (size_t)E * ldk * ldk * sizeof(double), st);
+    rc = gemm(st, E, Mi, Mi, Mi, 1, 0, 1.0, Linv, ldm, mm, Linv, ldm, mm, 0.0, iK, ldk, (long long)ldk * ldk);
+    if (rc) return rc;
+    // iK -= sn2[e] * iAt^T iAt
+    rc = gemm(st, E, Mi, Mi, Mi, 1, 0, 1.0, iAt, ldm, mm, iAt, ldm, mm, 0.0, T, ldm, mm);
+    if (rc) return rc;
+    fitc_axpy_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, E), dim3(32, 8), 0, st>>>(Mi, iK, ldk, (long long)ldk * ldk, T, ldm, mm, sn2);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+}  // extern "C"

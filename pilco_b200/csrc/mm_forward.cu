@@ -1,0 +1,81 @@
+// mm_forward.cu -- host side of pilco_mm_forward (C ABI) + shared launcher.
+#include "mm_kernels.cuh"
+
+int mm_check_model(const pilco_gp_model* gp) {
+    if (!gp || !gp->X || !gp->ell || !gp->sf2 || !gp->beta) return PILCO_ERR_NULL;
+    if (gp->n < 1 || gp->D < 1 || gp->D > MAXD || gp->E < 1 || gp->E > MAXE) return PILCO_ERR_DIM;
+    if (gp->mode != 0 && gp->mode != 1) return PILCO_ERR_DIM;
+    if (gp->mode == 0 && gp->iK) {
+        if (gp->ldk < pad64(gp->n) || (gp->ldk & 1)) return PILCO_ERR_DIM;
+        if (((uintptr_t)gp->iK) & 15) return PILCO_ERR_ALIGN;
+    }
+    return PILCO_OK;
+}
+
+template <int KS>
+static int launch_tile(const MMParams& p, cudaStream_t st) {
+    const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mm_tile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)mm_tile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        configured = true;
+    }
+    dim3 grid(p.L.NB, p.L.P, p.R);
+    mm_tile_kernel<KS><<<grid, 256, smem, st>>>(p);
+    return PILCO_OK;
+}
+
+int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
+    const int E = p.gp.E, D = p.gp.D;
+    dim3 gs(E + p.L.P, p.R);
+    const int ks = ksteps_of(D);
+    switch (ks) {
+        case 1: mm_setup_kernel<4><<<gs, 128, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8><<<gs, 128, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12><<<gs, 128, 0, st>>>(p); break;
+        default: mm_setup_kernel<16><<<gs, 128, 0, st>>>(p); break;
+    }
+    CUDA_LAUNCH_CHECK();
+    int rc;
+    switch (ks) {
+        case 1: rc = launch_tile<1>(p, st); break;
+        case 2: rc = launch_tile<2>(p, st); break;
+        case 3: rc = launch_tile<3>(p, st); break;
+        default: rc = launch_tile<4>(p, st); break;
+    }
+    if (rc) return rc;
+    CUDA_LAUNCH_CHECK();
+    if (with_finish) {
+        mm_finish_kernel<<<p.R, 128, 0, st>>>(p);
+        CUDA_LAUNCH_CHECK();
+    }
+    return PILCO_OK;
+}
+
+extern "C" {
+
+int pilco_pad_n(int n) { return pad64(n); }
+
+size_t pilco_mm_workspace_bytes(int n, int D, int E, int R) {
+    if (n < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || R < 1) return 0;
+    const MMWs L = mm_ws_layout(n, D, E);
+    return L.per_r * (size_t)R * sizeof(double);
+}
+
+int pilco_mm_forward(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                     double* M, double* S, double* V, int* info,
+                     void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    int rc = mm_check_model(gp);
+    if (rc) return rc;
+    if (!m || !s || !M || !S || !V || !ws) return PILCO_ERR_NULL;
+    if (R < 1) return PILCO_ERR_DIM;
+    if (ws_bytes < pilco_mm_workspace_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
+    if (((uintptr_t)ws) & 15) return PILCO_ERR_ALIGN;
+    MMParams p;
+    p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D; p.M = M; p.S = S; p.V = V; p.info = info;
+    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E);
+    return mm_forward_launch(p, (cudaStream_t)stream, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+"""Device-side plumbing: PyTorch owns every fp64 device buffer, the C ABI does the math.
+
+Each function mirrors one C entry point; arguments are numpy arrays or CUDA tensors, results are
+CUDA tensors (the API classes convert to host arrays at the boundary).  There is no CPU path:
+``device()`` raises when no CUDA device is present.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, GpModel
+
+F64 = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pilco_b200: a CUDA device (B200, sm_100a) is required; "
+                           "there is no CPU fallback for the moment-matching path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dev(x, dtype=F64):
+    """numpy / tensor -> contiguous CUDA tensor"""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float64)), dtype=dtype).to(device())
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def pad_n(n):
+    return int(lib.pilco_pad_n(int(n)))
+
+
+class DeviceGP:
+    """Device-resident factorised multi-output GP (what ``pilco_gp_model`` points at).
+
+    ``X`` [B?,n,D], ``ell`` [B?,E,D], ``sf2`` [B?,E], ``beta`` [B?,E,n]; a leading batch dimension
+    B (per-restart RBF policies) is optional and must match the rollout batch R.
+    """
+
+    def __init__(self, X, ell, sf2, beta, iK=None, ldk=0, mode=0, batched=False):
+        self.X, self.ell, self.sf2, self.beta, self.iK = X, ell, sf2, beta, iK
+        self.ldk, self.mode, self.batched = int(ldk), int(mode), bool(batched)
+        self.n, self.D = int(X.shape[-2]), int(X.shape[-1])
+        self.E = int(ell.shape[-2])
+
+    def struct(self):
+        g = GpModel()
+        g.n, g.D, g.E, g.mode = self.n, self.D, self.E, self.mode
+        b = self.batched
+        g.X = self.X.data_ptr(); g.X_bs = self.n * self.D if b else 0
+        g.ell = self.ell.data_ptr(); g.ell_bs = self.E * self.D if b else 0
+        g.sf2 = self.sf2.data_ptr(); g.sf2_bs = self.E if b else 0
+        g.beta = self.beta.data_ptr(); g.beta_bs = self.E * self.n if b else 0
+        g.iK = self.iK.data_ptr() if self.iK is not None else None
+        g.ldk = self.ldk
+        return g
+
+
+def gp_factorize(X, Y, ell, sf2, sn2, need_iK=True, mode=0):
+    """pilco_gp_factorize.  Unbatched inputs ([n,D], [n,E], [E,D], [E], [E]) or batched with a leading B."""
+    X, Y, ell, sf2, sn2 = dev(X), dev(Y), dev(ell), dev(sf2), dev(sn2)
+    batched = X.dim() == 3
+    B = X.shape[0] if batched else 1
+    n, D = X.shape[-2], X.shape[-1]
+    E = Y.shape[-1]
+    ldk = pad_n(n)
+    d = device()
+    beta = torch.empty((B, E, n) if batched else (E, n), dtype=F64, device=d)
+    iK = torch.empty((B, E, ldk, ldk) if batched else (E, ldk, ldk), dtype=F64, device=d) if need_iK else None
+    info = torch.zeros(B, dtype=torch.int32, device=d)
+    wsb = lib.pilco_gp_factorize_workspace_bytes(n, E, B)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    bs = lambda t, per: (per if batched else 0)
+    check(lib.pilco_gp_factorize(n, D, E, B,
+                                 ptr(X), bs(X, n * D), ptr(Y), bs(Y, n * E), ptr(ell), bs(ell, E * D),
+                                 ptr(sf2), bs(sf2, E), ptr(sn2), bs(sn2, E),
+                                 ptr(iK), ldk, ptr(beta), ptr(info), ptr(ws), wsb, stream_ptr()),
+          "gp_factorize")
+    gp = DeviceGP(X, ell, sf2, beta, iK, ldk, mode=mode, batched=batched)
+    gp.info = info
+    return gp
+
+
+def fitc_factorize(X, Z, Y, ell, sf2, sn2):
+    """pilco_fitc_factorize: FITC over inducing points Z -> DeviceGP centred on Z."""
+    X, Z, Y, ell, sf2, sn2 = dev(X), dev(Z), dev(Y), dev(ell), dev(sf2), dev(sn2)
+    N, D = X.shape
+    Mi = Z.shape[0]
+    E = Y.shape[1]
+    ldk = pad_n(Mi)
+    d = device()
+    beta = torch.empty((E, Mi), dtype=F64, device=d)
+    iK = torch.empty((E, ldk, ldk), dtype=F64, device=d)
+    info = torch.zeros(1, dtype=torch.int32, device=d)
+    wsb = lib.pilco_fitc_workspace_bytes(N, Mi, E)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    check(lib.pilco_fitc_factorize(N, Mi, D, E, ptr(X), ptr(Z), ptr(Y), ptr(ell), ptr(sf2), ptr(sn2),
+                                   ptr(iK), ldk, ptr(beta), ptr(info), ptr(ws), wsb, stream_ptr()),
+          "fitc_factorize")
+    gp = DeviceGP(Z, ell, sf2, beta, iK, ldk, mode=0)
+    gp.info = info
+    return gp
+
+
+def mm_forward(gp, m, s):
+    """pilco_mm_forward: m [R,D], s [R,D,D] -> M [R,E], S [R,E,E], V [R,D,E], info [R]."""
+    m, s = dev(m), dev(s)
+    R = m.shape[0]
+    d = device()
+    M = torch.empty((R, gp.E), dtype=F64, device=d)
+    S = torch.empty((R, gp.E, gp.E), dtype=F64, device=d)
+    V = torch.empty((R, gp.D, gp.E), dtype=F64, device=d)
+    info = torch.zeros(R, dtype=torch.int32, device=d)
+    wsb = lib.pilco_mm_workspace_bytes(gp.n, gp.D, gp.E, R)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    g = gp.struct()
+    check(lib.pilco_mm_forward(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(S), ptr(V), ptr(info),
+                               ptr(ws), wsb, stream_ptr()), "mm_forward")
+    return M, S, V, info
+
+
+def squash_sin(m, s, max_action):
+    m, s, e = dev(m), dev(s), dev(max_action)
+    R, U = m.shape
+    d = device()
+    M = torch.empty((R, U), dtype=F64, device=d)
+    S = torch.empty((R, U, U), dtype=F64, device=d)
+    Cq = torch.empty((R, U, U), dtype=F64, device=d)
+    check(lib.pilco_squash_sin(U, R, ptr(m), ptr(s), ptr(e), ptr(M), ptr(S), ptr(Cq), stream_ptr()), "squash_sin")
+    return M, S, Cq
+
+
+def linear_action(W, b, m, s):
+    W, b, m, s = dev(W), dev(b), dev(m), dev(s)
+    R, Ds = m.shape
+    U = W.shape[-2]
+    batched = W.dim() == 3
+    d = device()
+    M = torch.empty((R, U), dtype=F64, device=d)
+    S = torch.empty((R, U, U), dtype=F64, device=d)
+    V = torch.empty((R, Ds, U), dtype=F64, device=d)
+    check(lib.pilco_linear_action(Ds, U, R, ptr(W), U * Ds if batched else 0, ptr(b), U if batched else 0,
+                                  ptr(m), ptr(s), ptr(M), ptr(S), ptr(V), stream_ptr()), "linear_action")
+    return M, S, V
+
+
+def exp_reward(W, t, m, s, variance=True):
+    W, t, m, s = dev(W), dev(t), dev(m), dev(s)
+    R, Ds = m.shape
+    d = device()
+    mu = torch.empty(R, dtype=F64, device=d)
+    sR = torch.empty(R, dtype=F64, device=d) if variance else None
+    check(lib.pilco_exp_reward(Ds, R, ptr(W), ptr(t), ptr(m), ptr(s), ptr(mu), ptr(sR), None, stream_ptr()),
+          "exp_reward")
+    return mu, sR
+
+
+class RolloutPlan:
+    """Owns the buffers of one ``pilco_rollout`` description (batch R, horizon H) and launches it."""
+
+    def __init__(self, dyn, policy_spec, reward_terms, m0, S0, H, R=1):
+        d = device()
+        self.dyn = dyn
+        self.R, self.H = int(R), int(H)
+        self.Ds, self.U = policy_spec["Ds"], policy_spec["U"]
+        self.keep = [dyn, policy_spec, reward_terms]            # keep device tensors alive
+        ro = _lib.Rollout()
+        ro.R, ro.H = self.R, self.H
+        ro.dyn = dyn.struct()
+        pol = ro.pol
+        pol.kind = policy_spec["kind"]
+        pol.Ds, pol.U = self.Ds, self.U
+        pol.squash = 1 if policy_spec.get("squash", True) else 0
+        self.max_action = dev(np.broadcast_to(np.asarray(policy_spec.get("max_action", 1.0), dtype=np.float64).ravel(),
+                                              (self.U,)).copy())
+        pol.max_action = self.max_action.data_ptr()
+        if pol.kind == _lib.POLICY_LINEAR:
+            self.W, self.b = dev(policy_spec["W"]), dev(policy_spec["b"])
+            bat = self.W.dim() == 3
+            pol.W = self.W.data_ptr(); pol.W_bs = self.U * self.Ds if bat else 0
+            pol.b = self.b.data_ptr(); pol.b_bs = self.U if bat else 0
+        else:
+            self.rbf = policy_spec["gp"]
+            pol.rbf = self.rbf.struct()
+        self.rw = []
+        ro.n_rewards = len(reward_terms)
+        for k, rt in enumerate(reward_terms):
+            W = dev(rt["W"]); t = dev(rt["t"]) if rt.get("t") is not None else None
+            self.rw.append((W, t))
+            ro.rewards[k].kind = rt["kind"]
+            ro.rewards[k].coef = float(rt.get("coef", 1.0))
+            ro.rewards[k].W = W.data_ptr()
+            ro.rewards[k].t = t.data_ptr() if t is not None else None
+        self.m0, self.S0 = dev(m0), dev(S0)
+        bat0 = self.m0.dim() == 2 and self.m0.shape[0] == self.R and self.R > 1
+        self.m0 = self.m0.reshape(-1, self.Ds) if bat0 else self.m0.reshape(self.Ds)
+        ro.m0 = self.m0.data_ptr(); ro.m0_bs = self.Ds if bat0 else 0
+        batS = self.S0.dim() == 3
+        ro.S0 = self.S0.data_ptr(); ro.S0_bs = self.Ds * self.Ds if batS else 0
+        self.traj_m = torch.empty((self.R, self.H + 1, self.Ds), dtype=F64, device=d)
+        self.traj_S = torch.empty((self.R, self.H + 1, self.Ds, self.Ds), dtype=F64, device=d)
+        self.reward = torch.empty(self.R, dtype=F64, device=d)
+        self.step_reward = torch.empty((self.R, max(self.H, 1)), dtype=F64, device=d)
+        self.info = torch.zeros(self.R, dtype=torch.int32, device=d)
+        ro.traj_m, ro.traj_S = self.traj_m.data_ptr(), self.traj_S.data_ptr()
+        ro.reward, ro.step_reward, ro.info = self.reward.data_ptr(), self.step_reward.data_ptr(), self.info.data_ptr()
+        wsb = lib.pilco_rollout_workspace_bytes(C.byref(ro))
+        self.ws = torch.empty(max(wsb // 8, 2), dtype=F64, device=d)
+        ro.ws, ro.ws_bytes = self.ws.data_ptr(), wsb
+        self.ro = ro
+
+    def forward(self):
+        check(lib.pilco_rollout_forward(C.byref(self.ro), stream_ptr()), "rollout_forward")
+        return self.traj_m, self.traj_S, self.reward

@@ -1,0 +1,3 @@
+from .mgpr import MGPR
+from .smgpr import SMGPR
+from .pilco import PILCO

@@ -1,0 +1,130 @@
+"""PILCO orchestrator (drop-in for pilco/models/pilco.py:15-160).
+
+The H-step moment-matching cascade (``predict``/``propagate``, pilco.py:118-153) and the policy
+objective with its gradient run on the device through ``pilco_rollout_*``; policy optimisation batches
+the random restarts (pilco.py:98-107) in one device rollout and shards them across ranks
+(``pilco_b200.policy_opt``)."""
+import time
+
+import numpy as np
+import pandas as pd
+
+from .. import controllers, rewards, engine, _lib
+from ..params import host, set_trainable
+from .mgpr import MGPR
+from .smgpr import SMGPR
+
+
+class PILCO:
+    def __init__(self, data, num_induced_points=None, horizon=30, controller=None,
+                 reward=None, m_init=None, S_init=None, name=None):
+        self.name = name
+        if num_induced_points is None:
+            self.mgpr = MGPR(data)
+        else:
+            self.mgpr = SMGPR(data, num_induced_points)
+        self.state_dim = data[1].shape[1]
+        self.control_dim = data[0].shape[1] - data[1].shape[1]
+        self.horizon = horizon
+        self.controller = controller if controller is not None else \
+            controllers.LinearController(self.state_dim, self.control_dim)
+        self.reward = reward if reward is not None else rewards.ExponentialReward(self.state_dim)
+        if m_init is None or S_init is None:
+            # first state of the data set, pilco.py:36-41
+            self.m_init = data[0][0:1, 0:self.state_dim]
+            self.S_init = np.diag(np.ones(self.state_dim) * 0.1)
+        else:
+            self.m_init = m_init
+            self.S_init = S_init
+        self.optimizer = None
+
+    # ---- parameters ------------------------------------------------------------------------------
+    @property
+    def trainable_parameters(self):
+        return list(self.mgpr.trainable_parameters) + list(self.controller.trainable_parameters)
+
+    # ---- device rollout ---------------------------------------------------------------------------
+    def policy_spec(self, flats=None):
+        """Description of the policy for ``RolloutPlan``; ``flats`` [R,P] = per-restart flat parameters."""
+        c = self.controller
+        if isinstance(c, controllers.LinearController):
+            return c.policy_spec(flats)
+        if isinstance(c, controllers.RbfController):
+            bf, Ds, U = c.policy_shapes
+            if flats is None:
+                gp = c.device_gp()
+            else:
+                X, Y, th = c.split_flat(flats)
+                ell = 1e-3 + np.logaddexp(0.0, th)
+                R = X.shape[0]
+                gp = engine.gp_factorize(X, Y, ell, np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
+            return dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True,
+                        max_action=controllers._max_action_vec(c.max_action, U), gp=gp)
+        raise TypeError("unsupported controller type %r" % type(c))
+
+    def rollout_plan(self, m_x, s_x, n, flats=None):
+        R = 1 if flats is None else int(np.asarray(flats).shape[0])
+        return engine.RolloutPlan(self.mgpr.device_gp(), self.policy_spec(flats), self.reward.terms(),
+                                  np.asarray(m_x, dtype=np.float64).reshape(-1),
+                                  np.asarray(s_x, dtype=np.float64), int(n), R=R)
+
+    def predict(self, m_x, s_x, n):
+        """n-step cascade (pilco.py:118-136) -> (m [1,Ds], S [Ds,Ds], reward [1,1])."""
+        plan = self.rollout_plan(m_x, s_x, n)
+        traj_m, traj_S, reward = plan.forward()
+        if int(plan.info.max().item()):
+            raise RuntimeError("moment-matching rollout failed: covariance not positive definite")
+        return host(traj_m[0, -1:]), host(traj_S[0, -1]), host(reward.reshape(1, 1))
+
+    def propagate(self, m_x, s_x):
+        """one step (pilco.py:138-153) -> (M_x [1,Ds], S_x [Ds,Ds])"""
+        M, S, _ = self.predict(m_x, s_x, 1)
+        return M, S
+
+    def training_loss(self):
+        return -self.predict(self.m_init, self.S_init, self.horizon)[2]
+
+    def compute_reward(self):
+        return -self.training_loss()
+
+    @property
+    def maximum_log_likelihood_objective(self):
+        return -self.training_loss()
+
+    def compute_action(self, x_m):
+        return self.controller.compute_action(x_m, np.zeros([self.state_dim, self.state_dim]))[0]
+
+    # ---- model training (pilco.py:52-73) ------------------------------------------------------------
+    def optimize_models(self, maxiter=200, restarts=1):
+        self.mgpr.optimize(restarts=restarts)
+        lengthscales, variances, noises = {}, {}, {}
+        for i, model in enumerate(self.mgpr.models):
+            lengthscales['GP' + str(i)] = model.kernel.lengthscales.numpy()
+            variances['GP' + str(i)] = np.array([model.kernel.variance.numpy()])
+            noises['GP' + str(i)] = np.array([model.likelihood.variance.numpy()])
+        print('-----Learned models------')
+        pd.set_option('display.precision', 3)
+        print('---Lengthscales---')
+        print(pd.DataFrame(data=lengthscales))
+        print('---Variances---')
+        print(pd.DataFrame(data=variances))
+        print('---Noises---')
+        print(pd.DataFrame(data=noises))
+
+    # ---- policy optimisation (pilco.py:75-113) --------------------------------------------------------
+    def optimize_policy(self, maxiter=50, restarts=1):
+        from .. import policy_opt
+        start = time.time()
+        mgpr_trainable = self.mgpr.trainable_parameters
+        for p in mgpr_trainable:
+            set_trainable(p, False)
+        try:
+            best_flat, best_reward, all_rewards = policy_opt.optimize(self, maxiter=maxiter, restarts=restarts)
+            self.controller.set_flat(best_flat)
+        finally:
+            for p in mgpr_trainable:
+                set_trainable(p, True)
+        end = time.time()
+        for rwd in all_rewards:
+            print("Controller's optimization: done in %.1f seconds with reward=%.3f." % (end - start, rwd))
+        return best_reward
