@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- moment-match rollout steps/s of the B200-native PILCO engine (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--restarts R]
+
+One bench "step" = one pass of the hot path over one batch: an H-step moment-matching rollout
+(policy moment match -> squash -> joint -> dynamics moment match -> glue -> reward, pilco.py:118-153)
+for R independent policy restarts per GPU.  value = R*H*N_gpus rollout steps / second.
+
+Workload (metric config, BASELINE.json / SURVEY.md section 8d): N=300 training points, E=Ds=10, U=2, D=12, H=40,
+RBF policy with 50 basis functions, fp64, synthetic seeded data, R=32 restarts per GPU (weak scaling).
+
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference-equivalent CPU path
+(oracle/torch_port.py, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=300, Ds=10, U=2, H=40, bf=50)
+METRIC = "moment-match rollout steps/sec (N=300, E=10, H=40, fp64)"
+UNIT = "rollout-steps/s"
+EXP_FLOP_EQ = 22.0          # fp64 flop-equivalents of one exp: 11 fp64 instructions (10 FMA-class + 1 add), FMA = 2
+
+
+def make_workload(seed=0, R=32):
+    """Seeded synthetic problem (SURVEY.md 8d recipe).  Restart r uses RandomState(seed+1+r) so any
+    sharding over ranks produces the same per-restart policies."""
+    N, Ds, U, bf = CFG["N"], CFG["Ds"], CFG["U"], CFG["bf"]
+    D = Ds + U
+    rng = np.random.RandomState(seed)
+    X = rng.rand(N, D)
+    A = rng.rand(D, Ds)
+    Y = 0.05 * (np.sin(X).dot(A) + 1e-3 * (rng.rand(N, Ds) - 0.5))     # state differences
+    ell = 1.0 + rng.rand(Ds, D)
+    sf2 = 0.05 * (1.0 + rng.rand(Ds))
+    sn2 = 1e-3 * np.ones(Ds)
+    m0 = X[0, :Ds].copy()
+    S0 = 0.1 * np.eye(Ds)
+    W = np.eye(Ds)
+    t = np.zeros(Ds)
+    return dict(X=X, Y=Y, ell=ell, sf2=sf2, sn2=sn2, m0=m0, S0=S0, W=W, t=t)
+
+
+def make_policies(restart_ids, seed=0):
+    Ds, U, bf = CFG["Ds"], CFG["U"], CFG["bf"]
+    Xc, Yc, lc = [], [], []
+    for r in restart_ids:
+        rng = np.random.RandomState(seed + 1 + int(r))
+        Xc.append(rng.randn(bf, Ds) * 0.5 + 0.5)
+        Yc.append(0.1 * rng.randn(bf, U))
+        lc.append(1.0 + 0.1 * rng.randn(U, Ds))
+    return np.stack(Xc), np.stack(Yc), np.stack(lc)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle torch port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps_per_s(wl, reps=2, h_sample=4, threads=None):
+    import torch
+    from oracle import torch_port as tp
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    X, Y, ell, sf2, sn2 = map(T, (wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"]))
+    Xc, Yc, lc = make_policies([0])
+    Xc, Yc, lc = T(Xc[0]), T(Yc[0]), T(lc[0])
+    maxa = torch.ones((1, CFG["U"]), dtype=torch.float64)
+    W, t = T(wl["W"]), T(wl["t"])[None]
+    Ds = CFG["Ds"]
+
+    def one_rollout():
+        # the reference recomputes both factorisations inside every step (mgpr.py:77-79, controllers.py:115)
+        def dyn(m, s):
+            iK, beta = tp.calculate_factorizations(X, Y, ell, sf2, sn2)
+            return tp.predict_given_factorizations(X, ell, sf2, m, s, iK, beta)
+        act = lambda m, s: tp.rbf_action(Xc, Yc, lc, m, s, maxa)
+        rew = lambda m, s: tp.exponential_reward(m, s, W, t)
+        with torch.no_grad():
+            return tp.predict(T(wl["m0"])[None], T(wl["S0"]), h_sample, act, dyn, rew)
+
+    one_rollout()                       # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_rollout()
+    dt = time.perf_counter() - t0
+    return reps * h_sample / dt, threads, "R=1, %d rollouts of %d steps (of H=%d), factorisations recomputed per step as in the reference" % (reps, h_sample, CFG["H"])
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload()
+    # warm-up / steps map onto repetitions of a bounded sample
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_steps_per_s(wl, reps=1, h_sample=2)
+    t0 = time.perf_counter()
+    v, cores, sample = cpu_reference_steps_per_s(wl, reps=max(1, min(args.steps, 3)), h_sample=4)
+    dt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v * CFG["H"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "metric config N=300 E=10 D=12 H=40 RBF bf=50 (CPU sample: R=1)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference-equivalent CPU restatement (oracle/torch_port.py); TensorFlow/GPflow are not installable offline",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for nme, val in zip(names, s[2:]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pilco_b200 import engine, _lib
+    from pilco_b200._lib import lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    d = engine.device()
+    R, H = args.restarts, CFG["H"]
+    Ds, U, bf, N = CFG["Ds"], CFG["U"], CFG["bf"], CFG["N"]
+    D = Ds + U
+    wl = make_workload()
+    gp = engine.gp_factorize(wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"])      # once per set_data
+    my_ids = np.arange(rank * R, (rank + 1) * R)                                     # weak scaling: R per GPU
+    Xc, Yc, lc = make_policies(my_ids)
+    ones, noise = np.ones((R, U)), 1e-4 * np.ones((R, U))
+    maxa = np.ones(U)
+    rew = [dict(kind=_lib.REWARD_EXP, coef=1.0, W=wl["W"], t=wl["t"])]
+
+    # ---- device-resident arm: policy parameters already in HBM, rollout only --------------------------
+    pgp = engine.gp_factorize(Xc, Yc, lc, ones, noise, need_iK=False, mode=1)
+    spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pgp)
+    plan = engine.RolloutPlan(gp, spec, rew, wl["m0"], wl["S0"], H, R=R)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=d)       # > L2 (126 MB)
+    gathered = [torch.empty(R, dtype=torch.float64, device=d) for _ in range(world)]
+
+    def step_resident():
+        plan.forward()
+        if world > 1:
+            dist.all_gather(gathered, plan.reward)
+
+    # ---- end-to-end arm: host buffers in, host result out -----------------------------------------
+    hX = torch.as_tensor(Xc).pin_memory(); hY = torch.as_tensor(Yc).pin_memory(); hl = torch.as_tensor(lc).pin_memory()
+    dX = torch.empty_like(hX, device=d); dY = torch.empty_like(hY, device=d); dl = torch.empty_like(hl, device=d)
+    h_out = torch.empty(R, dtype=torch.float64).pin_memory()
+    h2d = (hX.numel() + hY.numel() + hl.numel()) * 8
+    d2h = R * 8
+    d_ones, d_noise = engine.dev(ones), engine.dev(noise)
+
+    def step_e2e():
+        dX.copy_(hX, non_blocking=True); dY.copy_(hY, non_blocking=True); dl.copy_(hl, non_blocking=True)
+        p2 = engine.gp_factorize(dX, dY, dl, d_ones, d_noise, need_iK=False, mode=1)
+        sp2 = dict(spec, gp=p2)
+        pl2 = engine.RolloutPlan(gp, sp2, rew, wl["m0"], wl["S0"], H, R=R)
+        pl2.forward()
+        h_out.copy_(pl2.reward, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pl2
+
+    def timed(fn, K, W):
+        for _ in range(W):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(K):
+            flush.fill_(1.0)                                   # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([tot], dtype=torch.float64, device=d)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
+        return float(t.item()) / K                             # ms per step
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    ok = int(plan.info.max().item()) == 0 and bool(torch.isfinite(plan.reward).all().item())
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    total_steps = R * H * world
+    value = total_steps / (ms_res * 1e-3)
+    e2e_value = total_steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (dynamics mm_tile) -------------------------------------------
+    ms3 = (C.c_float * 3)()
+    m_in = plan.ws[:R * D].clone()      # any finite inputs of the right shape: use the last joint Gaussian
+    from pilco_b200.engine import ptr, stream_ptr
+    g = gp.struct()
+    E = Ds
+    Mo = torch.empty((R, E), dtype=torch.float64, device=d); So = torch.empty((R, E, E), dtype=torch.float64, device=d)
+    Vo = torch.empty((R, D, E), dtype=torch.float64, device=d); info = torch.zeros(R, dtype=torch.int32, device=d)
+    wsb = lib.pilco_mm_workspace_bytes(N, D, E, R)
+    ws = torch.empty(wsb // 8, dtype=torch.float64, device=d)
+    mj = engine.dev(np.tile(np.concatenate([wl["m0"], np.zeros(U)]), (R, 1)))
+    sj = engine.dev(np.tile(0.1 * np.eye(D), (R, 1, 1)))
+    tile_ms, setup_ms = [], []
+    for i in range(8):
+        flush.fill_(1.0)
+        _lib.check(lib.pilco_mm_forward_profile(C.byref(g), R, ptr(mj), ptr(sj), ptr(Mo), ptr(So), ptr(Vo), ptr(info),
+                                                ptr(ws), wsb, ms3, stream_ptr()))
+        if i >= 3:
+            setup_ms.append(ms3[0]); tile_ms.append(ms3[1])
+    tile_ms = float(np.mean(tile_ms)); setup_ms = float(np.mean(setup_ms))
+    # fp64 pipe peaks measured live (DFMA and DMMA microbenchmarks, same process)
+    sink = torch.zeros(8, dtype=torch.float64, device=d)
+    msf = C.c_float()
+    iters, blocks = 20000, 148 * 4
+    _lib.check(lib.pilco_microbench_fp64(0, iters, blocks, ptr(sink), C.byref(msf), stream_ptr()))
+    dfma_tf = 2 * blocks * 256 * iters * 8.0 / (msf.value * 1e-3) / 1e12
+    _lib.check(lib.pilco_microbench_fp64(1, iters, blocks, ptr(sink), C.byref(msf), stream_ptr()))
+    dmma_tf = 2 * blocks * 8 * iters * 16.0 * 256 / (msf.value * 1e-3) / 1e12
+    P = E * (E + 1) // 2
+    elems = float(P) * N * N * R                                   # algorithmic pair-elements per launch
+    dot_flops = 2.0 * D * elems                                    # Q-contraction (DMMA)
+    other_flops = (4.0 + EXP_FLOP_EQ) * elems + 2.0 * E * N * N * R    # exponent assembly, exp, beta^T L beta, trace
+    flops = dot_flops + other_flops
+    achieved = flops / (tile_ms * 1e-3) / 1e12
+    peak_eff = flops / (dot_flops / dmma_tf + other_flops / dfma_tf)   # time-weighted fp64 peak for this op mix
+    alg_bytes = 8.0 * (E * N * N + R * (N * D + 2 * E * N + P * N * (D + 2)))   # iK once + per-restart operands
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {
+        "bound": "tensor", "kernel": "mm_tile_kernel<3> (dynamics GP, fp64 DMMA + DFMA/exp)",
+        "achieved": achieved, "peak": peak_eff, "unit": "TFLOP/s", "frac": achieved / peak_eff, "traffic": None,
+        "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), "
+                       "time-weighted for this kernel's op mix; MEASURED_PEAKS.json holds no fp64 figure" % (dfma_tf, dmma_tf),
+        "q_contraction_tflops": dot_flops / (tile_ms * 1e-3) / 1e12,
+        "tile_kernel_ms": tile_ms, "setup_kernel_ms": setup_ms,
+        "hbm": {"achieved_gbs": alg_bytes / (tile_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": alg_bytes / (tile_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+    }
+    cpu_v, cores, sample = cpu_reference_steps_per_s(wl, reps=2, h_sample=4)
+    launches_per_step = (H * 6 + 1) + 1                             # ro_state + policy(setup,tile,ro_policy) + dyn(setup,tile); +memset
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "metric config: N=300 E=Ds=10 U=2 D=12 H=40, RBF policy bf=50, R=%d restarts/GPU, forward rollout" % R,
+                   "restarts_per_gpu": R, "l2": "flushed between timed iterations (256 MiB write)", "finite": ok},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "what": "pinned host policy parameters -> device, policy factorisation, H-step rollout, rewards -> host"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "clocks": sampler.summary() if sampler else None,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--restarts", type=int, default=32, help="policy restarts per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,11 @@ int    pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream);
  * 1 DMMA m8n8k4, 2 both interleaved, 3 table exp, 4 libdevice exp; 8 ops/thread/iteration (16 DMMA for
  * which=1,2 counted as 8 pairs).  Synchronises (it times itself with CUDA events) -- never call it in a
  * captured region. */
+/* pilco_mm_forward with CUDA events around its three launches: ms_out[0..2] = setup, tile, finish.
+ * Synchronises. */
+int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                             double* M, double* S, double* V, int* info,
+                             void* ws, size_t ws_bytes, float* ms_out, pilco_stream_t stream);
 int pilco_microbench_fp64(int which, int iters, int blocks, double* sink_dev, float* ms_out, pilco_stream_t stream);
 
 #ifdef __cplusplus

@@ -68,6 +68,8 @@ SIGNATURES = {
     "pilco_exp_reward": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 8),
     "pilco_rollout_workspace_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
     "pilco_rollout_forward": (C.c_int, [C.POINTER(Rollout), c_dp]),
+    "pilco_mm_forward_profile": (C.c_int, [C.POINTER(GpModel), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                           c_dp, C.c_size_t, C.POINTER(C.c_float), c_dp]),
     "pilco_microbench_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, C.POINTER(C.c_float), c_dp]),
 }
 

@@ -78,4 +78,47 @@ int pilco_mm_forward(const pilco_gp_model* gp, int R, const double* m, const dou
     return mm_forward_launch(p, (cudaStream_t)stream, true);
 }
 
+// Diagnostic: same work as pilco_mm_forward, with CUDA events around the three launches
+// (ms_out[0..2] = setup, tile, finish).  Synchronises; never call it in a captured region.
+int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                             double* M, double* S, double* V, int* info,
+                             void* ws, size_t ws_bytes, float* ms_out, pilco_stream_t stream) {
+    int rc = mm_check_model(gp);
+    if (rc) return rc;
+    if (!m || !s || !M || !S || !V || !ws || !ms_out) return PILCO_ERR_NULL;
+    if (ws_bytes < pilco_mm_workspace_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
+    MMParams p;
+    p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D;
+    p.M = M; p.S = S; p.V = V; p.info = info;
+    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
+    const int E = gp->E, ks = ksteps_of(gp->D);
+    dim3 gs(E + p.L.P, R);
+    cudaEventRecord(ev[0], st);
+    switch (ks) {
+        case 1: mm_setup_kernel<4><<<gs, 128, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8><<<gs, 128, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12><<<gs, 128, 0, st>>>(p); break;
+        default: mm_setup_kernel<16><<<gs, 128, 0, st>>>(p); break;
+    }
+    cudaEventRecord(ev[1], st);
+    switch (ks) {
+        case 1: rc = launch_tile<1>(p, st); break;
+        case 2: rc = launch_tile<2>(p, st); break;
+        case 3: rc = launch_tile<3>(p, st); break;
+        default: rc = launch_tile<4>(p, st); break;
+    }
+    cudaEventRecord(ev[2], st);
+    mm_finish_kernel<<<R, 128, 0, st>>>(p);
+    cudaEventRecord(ev[3], st);
+    cudaEventSynchronize(ev[3]);
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    if (rc) return rc;
+    if (cudaGetLastError() != cudaSuccess) return PILCO_ERR_LAUNCH;
+    return PILCO_OK;
+}
+
 }  // extern "C"
