@@ -66,10 +66,38 @@ def make_policies(restart_ids, seed=0):
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: oracle torch port on the host cores
 # ------------------------------------------------------------------------------------------------
+_THREADS = None
+
+
+def pick_cpu_threads():
+    """All the host threads the CPU path can USE: torch's intra-op pool stops scaling (and on a shared
+    128-core box collapses) beyond a few tens of threads on these [E,E,N,N] elementwise ops, so calibrate
+    once on a small probe and keep the fastest of {8,16,32,64,all} <= os.cpu_count()."""
+    global _THREADS
+    if _THREADS is not None:
+        return _THREADS
+    import torch
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu} or {ncpu})
+    x = torch.rand(10, 10, 200, 200, dtype=torch.float64)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.exp(x)                                  # warm the pool
+        t0 = time.perf_counter()
+        for _ in range(3):
+            y = torch.exp(x + 1.0) @ x[0, 0]
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.9:                         # prefer fewer threads unless clearly faster
+            best, best_t = c, dt
+    _THREADS = best
+    return best
+
+
 def cpu_reference_steps_per_s(wl, reps=2, h_sample=4, threads=None):
     import torch
     from oracle import torch_port as tp
-    threads = threads or os.cpu_count()
+    threads = threads or pick_cpu_threads()
     torch.set_num_threads(threads)
     T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
     X, Y, ell, sf2, sn2 = map(T, (wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"]))
