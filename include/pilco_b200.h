@@ -67,12 +67,24 @@ int pilco_mm_forward(const pilco_gp_model* gp, int R,
                      int* info,             /* [R] or NULL */
                      void* ws, size_t ws_bytes, pilco_stream_t stream);
 
+/* VJP of pilco_mm_forward (the reference differentiates mgpr.py:91-149 with TensorFlow autodiff inside
+ * gpflow.optimizers.Scipy, pilco/models/pilco.py:84-90).  Inputs: the forward inputs m, s, the forward output
+ * M and the cotangents gM [R,E], gS [R,E,E], gV [R,D,E].  Outputs gm [R,D], gs [R,D,D] (symmetric part) and,
+ * when all three pointers are non-NULL (trainable RBF policy), gX [R,n,D], gbeta [R,E,n], gell [R,E,D]. */
+size_t pilco_mm_bwd_workspace_bytes(int n, int D, int E, int R, int need_param);
+int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const double* s, const double* M,
+                      const double* gM, const double* gS, const double* gV,
+                      double* gm, double* gs, double* gX, double* gbeta, double* gell,
+                      void* ws, size_t ws_bytes, pilco_stream_t stream);
+
 /* ---- GP factorisation -----------------------------------------------------------------------
  * Replaces MGPR.calculate_factorizations (pilco/models/mgpr.py:81-89; gp0.m:46-61):
  * K_e = sf2_e exp(-0.5 |(x-x')/ell_e|^2); L = chol(K + sn2_e I); iK = (K+sn2 I)^-1; beta = iK y_e.
  * B batch elements (B=1 for the dynamics GP; B=R for per-restart RBF policies).
  * iK is written with leading dimension ldk (zero padded; pass NULL to get beta only).
- * ws: scratch of pilco_gp_factorize_workspace_bytes(n, E, B) bytes.
+ * ws: scratch of pilco_gp_factorize_workspace_bytes(n, E, B) bytes; on return its first
+ * B*E*ldw*ldw doubles (ldw = pilco_pad_n(n)) hold the Cholesky factors L (lower triangles), which
+ * pilco_rollout_backward needs for the RBF policy (pilco_rollout_grad.pol_L).
  */
 size_t pilco_gp_factorize_workspace_bytes(int n, int E, int B);
 int pilco_gp_factorize(int n, int D, int E, int B,
@@ -168,6 +180,22 @@ typedef struct pilco_rollout {
 
 size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro);
 int    pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream);
+
+/* Reverse sweep: gradient of ro->reward[r] (= sum_t E[r(x_t)], the negative of PILCO.training_loss,
+ * pilco/models/pilco.py:47-50) with respect to the policy parameters.  Must follow pilco_rollout_forward
+ * with the same `ro` (the per-step joint Gaussians it saved in ro->ws are re-used).
+ * Linear policy: gW [R,U,Ds], gb [R,U].  RBF policy: gXc [R,bf,Ds] centres, gYc [R,bf,U] targets,
+ * gell [R,U,Ds] lengthscales (constrained), pol_L = Cholesky factors left by pilco_gp_factorize. */
+typedef struct pilco_rollout_grad {
+    double* gW; double* gb;
+    double* gXc; double* gYc; double* gell;
+    const double* pol_L;
+    double* gm0; double* gS0;       /* optional: gradient w.r.t. the initial state moments [R,Ds],[R,Ds,Ds] */
+    void* ws; size_t ws_bytes;
+} pilco_rollout_grad;
+
+size_t pilco_rollout_bwd_workspace_bytes(const pilco_rollout* ro);
+int    pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g, pilco_stream_t stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------
  * fp64 pipe microbenchmark used for the roofline denominators (DESIGN.md "Roofline"): which = 0 DFMA,

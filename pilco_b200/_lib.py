@@ -46,6 +46,12 @@ class Rollout(C.Structure):
                 ("info", c_dp), ("ws", c_dp), ("ws_bytes", C.c_size_t)]
 
 
+class RolloutGrad(C.Structure):
+    """mirror of ``pilco_rollout_grad``"""
+    _fields_ = [("gW", c_dp), ("gb", c_dp), ("gXc", c_dp), ("gYc", c_dp), ("gell", c_dp), ("pol_L", c_dp),
+                ("gm0", c_dp), ("gS0", c_dp), ("ws", c_dp), ("ws_bytes", C.c_size_t)]
+
+
 POLICY_LINEAR, POLICY_RBF = 0, 1
 REWARD_EXP, REWARD_LINEAR = 0, 1
 
@@ -68,6 +74,10 @@ SIGNATURES = {
     "pilco_exp_reward": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 8),
     "pilco_rollout_workspace_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
     "pilco_rollout_forward": (C.c_int, [C.POINTER(Rollout), c_dp]),
+    "pilco_mm_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "pilco_mm_backward": (C.c_int, [C.POINTER(GpModel), C.c_int] + [c_dp] * 11 + [c_dp, C.c_size_t, c_dp]),
+    "pilco_rollout_bwd_workspace_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
+    "pilco_rollout_backward": (C.c_int, [C.POINTER(Rollout), C.POINTER(RolloutGrad), c_dp]),
     "pilco_mm_forward_profile": (C.c_int, [C.POINTER(GpModel), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                            c_dp, C.c_size_t, C.POINTER(C.c_float), c_dp]),
     "pilco_microbench_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, C.POINTER(C.c_float), c_dp]),

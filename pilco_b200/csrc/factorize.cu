@@ -286,15 +286,16 @@ __global__ void __launch_bounds__(32) matvec_kernel(int m, int k, int ta, const 
 
 // Solve L L^T x = y for one right-hand side per matrix by blocked substitution (one CTA per matrix).
 // L lower triangular [n,n] (ld), y stride yinc, x contiguous [n].
-// Matrix z = b*E + e takes its right-hand side from column e of Y_b ([n,E], batch stride Y_bs).
+// Matrix z = b*E + e takes its right-hand side at Y + b*Y_bs + e*y_es with element increment yinc
+// (column e of an [n,E] array: y_es=1, yinc=E; row e of an [E,n] array: y_es=n, yinc=1).
 __global__ void __launch_bounds__(256) chol_solve_vec_kernel(int n, const double* Lall, int ld, long long ms,
                                                              int E, const double* Y, long long Y_bs,
+                                                             long long y_es, int yinc,
                                                              double* xall, long long xs) {
     extern __shared__ double sx[];            // n doubles
     __shared__ double sD[FB][FB + 1];
     const double* L = Lall + (size_t)blockIdx.x * ms;
-    const double* y = Y + (size_t)(blockIdx.x / E) * Y_bs + (blockIdx.x % E);
-    const int yinc = E;
+    const double* y = Y + (size_t)(blockIdx.x / E) * Y_bs + (size_t)(blockIdx.x % E) * y_es;
     double* x = xall + (size_t)blockIdx.x * xs;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < n; i += 256) sx[i] = y[(size_t)i * yinc];
@@ -385,6 +386,11 @@ __global__ void fitc_axpy_kernel(int n, double* C, int ldc, long long cs, const 
     if (i < n && j < n) C[(size_t)e * cs + (size_t)i * ldc + j] -= a[e] * Tm[(size_t)e * ts + (size_t)i * ldt + j];
 }
 
+void chol_solve_vec_launch(cudaStream_t st, int batch, int n, const double* L, int ld, long long ms, int E,
+                           const double* Y, long long Y_bs, long long y_es, int yinc, double* x, long long xs) {
+    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ld, ms, E, Y, Y_bs, y_es, yinc, x, xs);
+}
+
 extern "C" {
 
 size_t pilco_gp_factorize_workspace_bytes(int n, int E, int B) {
@@ -418,7 +424,7 @@ int pilco_gp_factorize(int n, int D, int E, int B,
     chol_kernel<<<batch, 256, 0, st>>>(n, L, ldw, ms, E, info);
     CUDA_LAUNCH_CHECK();
     // beta = (L L^T)^-1 y_e   (mgpr.py:86-88)
-    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ldw, ms, E, Y, Y_bs, beta, n);
+    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ldw, ms, E, Y, Y_bs, 1, E, beta, n);
     CUDA_LAUNCH_CHECK();
     if (iK) {
         // iK = L^-T L^-1 through the explicit triangular inverse (mgpr.py:85)

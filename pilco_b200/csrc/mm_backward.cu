@@ -1,0 +1,532 @@
+// mm_backward.cu -- hand-derived VJP of the SE-ARD moment match (the reference differentiates
+// pilco/models/mgpr.py:91-149 with TensorFlow autodiff; see oracle/staged.py:mm_backward_staged for the
+// numpy statement of exactly this algorithm and DESIGN.md "Backward").
+//
+//   bsetup  grid (E*E, R)     : mm_setup_kernel<DP,true>: ordered pairs, also stores Q_ab, C_ab, logdetR_ab
+//   btile   grid (NB, E*E, R) : recompute L'[n,m] tile-wise; per row n:  hL = sum_m beta_b[m] L',
+//                               HVL = sum_m beta_b[m] L' zeta_m  (+ hK, HVK with iK_a[n,m] on diagonal pairs)
+//   bfinish grid (E + E*E, R) : per task partial gradients (mean/V block per output, covariance block per pair)
+//   breduce grid (R)          : sums the task partials -> gm, gs (+ gX, gbeta, gell for trainable policies)
+#include "mm_backward.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// backward tile kernel
+// -------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
+    constexpr int DP = 4 * KS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const MMParams& p = bp.f;
+    const MMWs& L = bp.B.F;
+    const int np = L.np, ldz = L.ldz, E = p.gp.E;
+    const int CM = np < TILE_CM ? np : TILE_CM;
+    double* sZ = reinterpret_cast<double*>(smem_raw);
+    double* sBq = sZ + (size_t)CM * ldz;
+    double* sBe = sBq + CM;
+    double* tab = sBe + CM;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
+
+    const int r = blockIdx.z, q = blockIdx.y, rb = blockIdx.x;
+    const int a = q / E, b = q % E;
+    double* wsr = p.ws + (size_t)r * bp.B.per_r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int row0 = rb * 64 + warp * 8;
+    const int row = row0 + g;
+    const bool active = row0 < p.gp.n;
+
+    double ua[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)q * np + row) * ldz + 4 * ks + t];
+    const double Apv = wsr[L.Ap + (size_t)q * np + row];
+    const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
+    const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+
+    exp_table_init(tab);
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+
+    double accL[DP + 1], accK[DP + 1];
+#pragma unroll
+    for (int i = 0; i <= DP; ++i) { accL[i] = 0.0; accK[i] = 0.0; }
+    unsigned phase = 0;
+    for (int c0 = 0; c0 < np; c0 += CM) {
+        const int cm = (np - c0) < CM ? (np - c0) : CM;
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16));
+            tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
+            tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
+            tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (active) {
+            for (int col = 0; col < cm; col += 8) {
+                const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
+                double e0 = Apv + bq.x, e1 = Apv + bq.y;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
+                    dmma884(e0, e1, ua[ks], bf);
+                }
+                const double l0 = exp_tab(e0, tab), l1 = exp_tab(e1, tab);
+                const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
+                const double w0 = bb.x * l0, w1 = bb.y * l1;
+                const double* z0 = sZ + (size_t)(col + 2 * t) * ldz;
+                const double* z1 = z0 + ldz;
+                accL[DP] += w0 + w1;
+#pragma unroll
+                for (int d = 0; d < DP; d += 2) {
+                    const double2 za = *reinterpret_cast<const double2*>(z0 + d);
+                    const double2 zb = *reinterpret_cast<const double2*>(z1 + d);
+                    accL[d] = fma(w0, za.x, fma(w1, zb.x, accL[d]));
+                    accL[d + 1] = fma(w0, za.y, fma(w1, zb.y, accL[d + 1]));
+                }
+                if (diag) {
+                    const double2 ik = *reinterpret_cast<const double2*>(ikrow + c0 + col + 2 * t);
+                    const double v0 = ik.x * l0, v1 = ik.y * l1;
+                    accK[DP] += v0 + v1;
+#pragma unroll
+                    for (int d = 0; d < DP; d += 2) {
+                        const double2 za = *reinterpret_cast<const double2*>(z0 + d);
+                        const double2 zb = *reinterpret_cast<const double2*>(z1 + d);
+                        accK[d] = fma(v0, za.x, fma(v1, zb.x, accK[d]));
+                        accK[d + 1] = fma(v0, za.y, fma(v1, zb.y, accK[d + 1]));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // quad reduction (4 lanes share a row), then the quad writes the row's outputs
+    double* out = wsr + bp.B.rowout + ((size_t)q * np + row) * bp.B.ldr;
+#pragma unroll
+    for (int i = 0; i <= DP; ++i) {
+        double v = accL[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        double k = accK[i];
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        // layout: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK
+        const int slotL = (i == DP) ? 0 : 1 + i;
+        const int slotK = (i == DP) ? DP + 1 : DP + 2 + i;
+        if ((i & 3) == t) { out[slotL] = active ? v : 0.0; out[slotK] = active ? k : 0.0; }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward finish: one CTA (128 threads) per task
+// -------------------------------------------------------------------------------------------------
+#define BF_CHUNK 128
+
+template <int DP>
+__global__ void __launch_bounds__(128) mm_bfinish_kernel(MMBwdParams bp) {
+    const MMParams& p = bp.f;
+    const pilco_gp_model& gp = p.gp;
+    const MMBws& B = bp.B;
+    const MMWs& L = B.F;
+    const int n = gp.n, D = gp.D, E = gp.E, np = L.np, ldz = L.ldz;
+    const int r = blockIdx.y, task = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    __shared__ double sW[MAXD * SLD];         // W_a (output task) or Q_ab (pair task)
+    __shared__ double sCm[MAXD * SLD];        // C_ab (pair) / scratch
+    __shared__ double sT[MAXD * SLD];         // scratch
+    __shared__ double sinvd[MAXD];
+    __shared__ double spa[MAXD], spb[MAXD], sgv[MAXD], swgv[MAXD];
+    __shared__ double sred[(2 * MAXD + 2) * 4], sout[2 * MAXD + 2];
+    __shared__ double sOm[MAXD * MAXD];
+    __shared__ double sRowA[BF_CHUNK][DP + 1];   // za_n (pair) / (gw w) zeta_n (output)
+    __shared__ double sRowB[BF_CHUNK][DP + 1];   // w_n  (pair) / zeta_n (output)
+    __shared__ double sscal[4];
+
+    const double* ell = gp.ell + (size_t)r * gp.ell_bs;
+    const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
+    const double* beta = gp.beta + (size_t)r * gp.beta_bs;
+    double* wsr = p.ws + (size_t)r * B.per_r;
+    const double* zeta = wsr + L.zeta;
+    const double* gS = bp.gS + (size_t)r * E * E;
+    double* Tm = wsr + B.Tm + (size_t)task * MAXD;
+    double* Ts = wsr + B.Ts + (size_t)task * D * D;
+    double* Tpa = wsr + B.Tpa + (size_t)task * MAXD;
+    double* Tpb = wsr + B.Tpb + (size_t)task * MAXD;
+    double* Tz = wsr + B.Tz + (size_t)task * np * MAXD;
+    double* Tb = wsr + B.Tb + (size_t)task * np;
+    for (int e = tid; e < DP * DP; e += blockDim.x) sOm[e] = 0.0;
+
+    if (task < E) {
+        // ================= mean / V block of output a =================
+        const int a = task;
+        const double* sr = p.s + (size_t)r * p.s_rs;
+        if (tid < DP) {
+            const double l = tid < D ? ell[a * D + tid] : 1.0;
+            spa[tid] = l * l;
+            sgv[tid] = tid < D ? bp.gV[((size_t)r * D + tid) * E + a] : 0.0;
+        }
+        __syncthreads();
+        for (int e = tid; e < DP * DP; e += blockDim.x) {
+            const int i = e / DP, j = e % DP;
+            const double sij = (i < D && j < D) ? 0.5 * (sr[i * D + j] + sr[j * D + i]) : 0.0;
+            sT[i * SLD + j] = sij + (i == j ? spa[i] : 0.0);
+            sW[i * SLD + j] = (i == j) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            chol_warp(sT, sinvd, DP, lane);
+            chol_solve_warp(sT, sinvd, sW, DP, DP, lane);
+            if (lane == 0) {
+                double ld = chol_logdet(sinvd, DP), sl = 0.0;
+                for (int d = 0; d < D; ++d) sl += log(spa[d]);
+                sscal[0] = exp(log(sf2[a]) + 0.5 * (sl - ld));           // c_a
+                // gMtot[a] = gM[a] - sum_b (gS[a,b] + gS[b,a]) M_b
+                double gmt = bp.gM[(size_t)r * E + a];
+                for (int bb = 0; bb < E; ++bb) gmt -= (gS[a * E + bb] + gS[bb * E + a]) * p.M[(size_t)r * E + bb];
+                sscal[1] = gmt;
+            }
+        }
+        __syncthreads();
+        if (tid < DP) {                       // W gV_a
+            double v = 0.0;
+            for (int j = 0; j < DP; ++j) v = fma(sW[tid * SLD + j], sgv[j], v);
+            swgv[tid] = v;
+        }
+        __syncthreads();
+        const double ca = sscal[0], gmt = sscal[1];
+        double acc[2 * DP + 1];               // [0..DP) sum gzeta, [DP..2DP) y, [2DP] glogc
+#pragma unroll
+        for (int i = 0; i <= 2 * DP; ++i) acc[i] = 0.0;
+        for (int c0 = 0; c0 < np; c0 += BF_CHUNK) {
+            const int nn = c0 + tid;
+            double z[DP], gww = 0.0;
+#pragma unroll
+            for (int d = 0; d < DP; ++d) z[d] = 0.0;
+            if (nn < n) {
+                double tt[DP], e = 0.0, tg = 0.0;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = d < ldz ? zeta[(size_t)nn * ldz + d] : 0.0;
+#pragma unroll
+                for (int i = 0; i < DP; ++i) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) v = fma(sW[i * SLD + j], z[j], v);
+                    tt[i] = v; e = fma(z[i], v, e); tg = fma(v, sgv[i], tg);
+                }
+                const double qv = exp(-0.5 * e);
+                const double w = beta[(size_t)a * n + nn] * qv * ca;
+                const double gw = gmt + tg;
+                gww = gw * w;
+                acc[2 * DP] += gww;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) {
+                    const double gz = -gww * tt[d] + w * swgv[d];
+                    acc[d] += gz;
+                    acc[DP + d] = fma(w, z[d], acc[DP + d]);
+                    if (bp.need_param) Tz[(size_t)nn * MAXD + d] = gz;
+                }
+                if (bp.need_param) Tb[nn] = gw * qv * ca;
+            } else if (bp.need_param && nn < np) {
+                for (int d = 0; d < DP; ++d) Tz[(size_t)nn * MAXD + d] = 0.0;
+                Tb[nn] = 0.0;
+            }
+#pragma unroll
+            for (int d = 0; d < DP; ++d) { sRowA[tid][d] = gww * z[d]; sRowB[tid][d] = z[d]; }
+            __syncthreads();
+            for (int e = tid; e < DP * DP; e += blockDim.x) {       // sum_n (gw w zeta)[i] zeta[j]
+                const int i = e / DP, j = e % DP;
+                double v = sOm[e];
+                for (int k = 0; k < BF_CHUNK; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
+                sOm[e] = v;
+            }
+            __syncthreads();
+        }
+        block_sum<2 * MAXD + 2>(acc, 2 * DP + 1, sred, sout);
+        const double glogc = sout[2 * DP];
+        // gW = -0.5 sOm + sym(gV y^T);  gA = -W gW W - 0.5 glogc W
+        for (int e = tid; e < DP * DP; e += blockDim.x) {
+            const int i = e / DP, j = e % DP;
+            sT[i * SLD + j] = -0.5 * sOm[e] + 0.5 * (sgv[i] * sout[DP + j] + sgv[j] * sout[DP + i]);
+        }
+        __syncthreads();
+        for (int e = tid; e < DP * DP; e += blockDim.x) {           // sCm = W gW
+            const int i = e / DP, j = e % DP;
+            double v = 0.0;
+            for (int k = 0; k < DP; ++k) v = fma(sW[i * SLD + k], sT[k * SLD + j], v);
+            sCm[i * SLD + j] = v;
+        }
+        __syncthreads();
+        for (int e = tid; e < D * D; e += blockDim.x) {
+            const int i = e / D, j = e % D;
+            double v = 0.0;
+            for (int k = 0; k < DP; ++k) v = fma(sCm[i * SLD + k], sW[k * SLD + j], v);
+            const double ga = -v - 0.5 * glogc * sW[i * SLD + j];
+            Ts[e] = ga;
+            if (i == j) Tpa[i] = ga + 0.5 * glogc / spa[i];         // g(ell_a^2)
+        }
+        if (tid < DP) { Tm[tid] = -sout[tid]; Tpb[tid] = 0.0; }
+        return;
+    }
+
+    // ================= covariance block of the ordered pair (a,b), row side =================
+    const int q = task - E;
+    const int a = q / E, b = q % E;
+    const double gt = gS[a * E + b] + gS[b * E + a];
+    const double* Qg = wsr + B.oQ + (size_t)q * D * D;
+    const double* Cg = wsr + B.oC + (size_t)q * D * D;
+    if (tid < DP) {
+        const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
+        spa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
+        spb[tid] = tid < D ? 1.0 / (lb * lb) : 0.0;
+    }
+    for (int e = tid; e < DP * DP; e += blockDim.x) {
+        const int i = e / DP, j = e % DP;
+        const bool in = i < D && j < D;
+        sW[i * SLD + j] = in ? Qg[i * D + j] : 0.0;
+        sCm[i * SLD + j] = in ? Cg[i * D + j] : 0.0;
+    }
+    __syncthreads();
+    const bool diag = (a == b) && (gp.mode == 0) && (gp.iK != nullptr);
+    double acc[2 * DP + 1];                   // [0..DP) sum gzeta_n ; [DP..2DP) row part of g p_a ; [2DP] T
+#pragma unroll
+    for (int i = 0; i <= 2 * DP; ++i) acc[i] = 0.0;
+    for (int c0 = 0; c0 < np; c0 += BF_CHUNK) {
+        const int nn = c0 + tid;
+        double za[DP], wv[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { za[d] = 0.0; wv[d] = 0.0; }
+        if (nn < n) {
+            const double* ro = wsr + B.rowout + ((size_t)q * np + nn) * B.ldr;
+            const double ba = beta[(size_t)a * n + nn];
+            const double hL = ro[0];
+            double hr = ba * hL;
+            if (diag) hr -= ro[DP + 1];
+            double z[DP];
+#pragma unroll
+            for (int d = 0; d < DP; ++d) {
+                z[d] = d < ldz ? zeta[(size_t)nn * ldz + d] : 0.0;
+                double hv = ba * ro[1 + d];
+                if (diag) hv -= ro[DP + 2 + d];
+                za[d] = spa[d] * z[d];
+                wv[d] = hr * za[d] + spb[d] * hv;               // hr za_n + p_b o HV_n
+            }
+            acc[2 * DP] += hr;
+#pragma unroll
+            for (int i = 0; i < DP; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < DP; ++j) v = fma(sW[i * SLD + j], wv[j], v);
+                const double gza = 2.0 * v;
+                const double gz = gt * (spa[i] * gza - hr * za[i]);
+                acc[i] += gz;
+                acc[DP + i] += gza * z[i] - 0.5 * hr * z[i] * z[i];
+                if (bp.need_param) Tz[(size_t)nn * MAXD + i] = gz;
+            }
+            if (bp.need_param) Tb[nn] = gt * hL;
+        } else if (bp.need_param && nn < np) {
+            for (int d = 0; d < DP; ++d) Tz[(size_t)nn * MAXD + d] = 0.0;
+            Tb[nn] = 0.0;
+        }
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { sRowA[tid][d] = za[d]; sRowB[tid][d] = wv[d]; }
+        __syncthreads();
+        for (int e = tid; e < DP * DP; e += blockDim.x) {           // Omega^r += sum_n za_n[i] w_n[j]
+            const int i = e / DP, j = e % DP;
+            double v = sOm[e];
+            for (int k = 0; k < BF_CHUNK; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
+            sOm[e] = v;
+        }
+        __syncthreads();
+    }
+    block_sum<2 * MAXD + 2>(acc, 2 * DP + 1, sred, sout);
+    const double T = sout[2 * DP];
+    const double glogR = -0.25 * gt * T;
+    // gQ = gt sym(Om) -> sT ;  G2 = gQ / (delta_i delta_j) -> reuse sOm as plain storage after sync
+    for (int e = tid; e < DP * DP; e += blockDim.x) {
+        const int i = e / DP, j = e % DP;
+        sT[i * SLD + j] = 0.5 * gt * (sOm[i * DP + j] + sOm[j * DP + i]);
+    }
+    __syncthreads();
+    // gs_pair = 0.5 C (gQ/dd) C + glogR C
+    __shared__ double sX[MAXD * SLD];
+    for (int e = tid; e < DP * DP; e += blockDim.x) {               // sX = C (gQ/dd)
+        const int i = e / DP, j = e % DP;
+        double v = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double dk = spa[k] + spb[k], dj = (j < D) ? spa[j] + spb[j] : 1.0;
+            v = fma(sCm[i * SLD + k], sT[k * SLD + j] / (dk * dj), v);
+        }
+        sX[i * SLD + j] = (j < D) ? v : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e % D;
+        double v = 0.0;
+        for (int k = 0; k < D; ++k) v = fma(sX[i * SLD + k], sCm[k * SLD + j], v);
+        Ts[e] = 0.5 * v + glogR * sCm[i * SLD + j];
+    }
+    // gdelta = -2 diag(Q gQ Q) + 2 glogR diag(Q)
+    if (tid < DP) {
+        double gd = 0.0;
+        if (tid < D) {
+            for (int k = 0; k < D; ++k) {
+                double v = 0.0;
+                for (int l = 0; l < D; ++l) v = fma(sT[k * SLD + l], sW[l * SLD + tid], v);    // (gQ Q)[k][i]
+                gd = fma(sW[tid * SLD + k], v, gd);
+            }
+            gd = -2.0 * gd + 2.0 * glogR * sW[tid * SLD + tid];
+        }
+        Tm[tid] = -sout[tid];
+        Tpa[tid] = gt * sout[DP + tid] + gd;        // contribution to g p_a
+        Tpb[tid] = gd;                              // contribution to g p_b
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// reduce: sum task partials
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mm_breduce_kernel(MMBwdParams bp) {
+    const MMParams& p = bp.f;
+    const pilco_gp_model& gp = p.gp;
+    const MMBws& B = bp.B;
+    const int n = gp.n, D = gp.D, E = gp.E, np = B.F.np;
+    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* wsr = p.ws + (size_t)r * B.per_r;
+    const double* ell = gp.ell + (size_t)r * gp.ell_bs;
+    double* gm = bp.gm + (size_t)r * bp.gm_rs;
+    double* gs = bp.gs + (size_t)r * bp.gs_rs;
+    for (int d = tid; d < D; d += nt) {
+        double v = 0.0;
+        for (int tk = 0; tk < B.ntask; ++tk) v += wsr[B.Tm + (size_t)tk * MAXD + d];
+        gm[d] = bp.accumulate ? gm[d] + v : v;
+    }
+    for (int e = tid; e < D * D; e += nt) {
+        const int i = e / D, j = e % D;
+        double v = 0.0;
+        for (int tk = 0; tk < B.ntask; ++tk)
+            v += 0.5 * (wsr[B.Ts + (size_t)tk * D * D + i * D + j] + wsr[B.Ts + (size_t)tk * D * D + j * D + i]);
+        gs[e] = bp.accumulate ? gs[e] + v : v;
+    }
+    if (!bp.need_param) return;
+    double* gX = bp.gX + (size_t)r * n * D;
+    double* gbeta = bp.gbeta + (size_t)r * E * n;
+    double* gell = bp.gell + (size_t)r * E * D;
+    for (int e = tid; e < n * D; e += nt) {
+        const int nn = e / D, d = e % D;
+        double v = 0.0;
+        for (int tk = 0; tk < B.ntask; ++tk) v += wsr[B.Tz + ((size_t)tk * np + nn) * MAXD + d];
+        gX[e] = bp.accumulate ? gX[e] + v : v;
+    }
+    for (int e = tid; e < E * n; e += nt) {
+        const int a = e / n, nn = e % n;
+        double v = wsr[B.Tb + (size_t)a * np + nn];
+        for (int b = 0; b < E; ++b) v += wsr[B.Tb + (size_t)(E + a * E + b) * np + nn];
+        gbeta[e] = bp.accumulate ? gbeta[e] + v : v;
+    }
+    for (int e = tid; e < E * D; e += nt) {
+        const int a = e / D, d = e % D;
+        double gp_ = 0.0;
+        for (int b = 0; b < E; ++b) {
+            gp_ += wsr[B.Tpa + (size_t)(E + a * E + b) * MAXD + d];      // row side of (a,b) + delta share
+            gp_ += wsr[B.Tpb + (size_t)(E + b * E + a) * MAXD + d];      // delta share of (b,a)
+        }
+        const double l = ell[a * D + d];
+        const double v = -2.0 * gp_ / (l * l * l) + 2.0 * l * wsr[B.Tpa + (size_t)a * MAXD + d];
+        gell[e] = bp.accumulate ? gell[e] + v : v;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// host
+// -------------------------------------------------------------------------------------------------
+template <int KS>
+static int launch_btile(const MMBwdParams& bp, cudaStream_t st) {
+    const size_t smem = mm_tile_smem_bytes(bp.B.F.np, bp.B.F.ldz);
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(mm_btile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)mm_tile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        configured = true;
+    }
+    dim3 grid(bp.B.F.NB, bp.B.P2, bp.f.R);
+    mm_btile_kernel<KS><<<grid, 256, smem, st>>>(bp);
+    return PILCO_OK;
+}
+
+int mm_backward_launch(MMBwdParams bp, cudaStream_t st) {
+    const int E = bp.f.gp.E, R = bp.f.R;
+    const int ks = ksteps_of(bp.f.gp.D);
+    MMParams sp = bp.f;                       // setup in ordered/backward mode on the same workspace
+    sp.L = bp.B.F; sp.bwd = 1; sp.oQ = bp.B.oQ; sp.oC = bp.B.oC; sp.oLd = bp.B.oLd;
+    // per-restart stride of the setup arrays must be the backward stride
+    sp.L.per_r = bp.B.per_r;
+    dim3 gs(E * E, R);
+    switch (ks) {
+        case 1: mm_setup_kernel<4, true><<<gs, 128, 0, st>>>(sp); break;
+        case 2: mm_setup_kernel<8, true><<<gs, 128, 0, st>>>(sp); break;
+        case 3: mm_setup_kernel<12, true><<<gs, 128, 0, st>>>(sp); break;
+        default: mm_setup_kernel<16, true><<<gs, 128, 0, st>>>(sp); break;
+    }
+    CUDA_LAUNCH_CHECK();
+    int rc;
+    switch (ks) {
+        case 1: rc = launch_btile<1>(bp, st); break;
+        case 2: rc = launch_btile<2>(bp, st); break;
+        case 3: rc = launch_btile<3>(bp, st); break;
+        default: rc = launch_btile<4>(bp, st); break;
+    }
+    if (rc) return rc;
+    CUDA_LAUNCH_CHECK();
+    dim3 gf(E + E * E, R);
+    switch (ks) {
+        case 1: mm_bfinish_kernel<4><<<gf, 128, 0, st>>>(bp); break;
+        case 2: mm_bfinish_kernel<8><<<gf, 128, 0, st>>>(bp); break;
+        case 3: mm_bfinish_kernel<12><<<gf, 128, 0, st>>>(bp); break;
+        default: mm_bfinish_kernel<16><<<gf, 128, 0, st>>>(bp); break;
+    }
+    CUDA_LAUNCH_CHECK();
+    mm_breduce_kernel<<<R, 128, 0, st>>>(bp);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+MMBwdParams mm_bwd_params(const pilco_gp_model* gp, int R, const double* m, long long m_rs, const double* s, long long s_rs,
+                          const double* Mfwd, const double* gM, const double* gS, const double* gV,
+                          double* gm, long long gm_rs, double* gs, long long gs_rs,
+                          double* gX, double* gbeta, double* gell, int accumulate, double* ws) {
+    MMBwdParams bp;
+    bp.need_param = (gX && gbeta && gell) ? 1 : 0;
+    bp.B = mm_bws_layout(gp->n, gp->D, gp->E, bp.need_param);
+    bp.f.gp = *gp; bp.f.R = R; bp.f.m = m; bp.f.s = s; bp.f.m_rs = m_rs; bp.f.s_rs = s_rs;
+    bp.f.M = const_cast<double*>(Mfwd); bp.f.S = nullptr; bp.f.V = nullptr; bp.f.info = nullptr;
+    bp.f.ws = ws; bp.f.L = bp.B.F; bp.f.bwd = 1; bp.f.oQ = bp.B.oQ; bp.f.oC = bp.B.oC; bp.f.oLd = bp.B.oLd;
+    bp.gM = gM; bp.gS = gS; bp.gV = gV;
+    bp.gm = gm; bp.gs = gs; bp.gm_rs = gm_rs; bp.gs_rs = gs_rs;
+    bp.gX = gX; bp.gbeta = gbeta; bp.gell = gell; bp.accumulate = accumulate;
+    return bp;
+}
+
+extern "C" {
+
+size_t pilco_mm_bwd_workspace_bytes(int n, int D, int E, int R, int need_param) {
+    if (n < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || R < 1) return 0;
+    return mm_bws_layout(n, D, E, need_param).per_r * (size_t)R * sizeof(double);
+}
+
+int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const double* s, const double* M,
+                      const double* gM, const double* gS, const double* gV,
+                      double* gm, double* gs, double* gX, double* gbeta, double* gell,
+                      void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    int rc = mm_check_model(gp);
+    if (rc) return rc;
+    if (!m || !s || !M || !gM || !gS || !gV || !gm || !gs || !ws) return PILCO_ERR_NULL;
+    if (R < 1) return PILCO_ERR_DIM;
+    const int need_param = (gX && gbeta && gell) ? 1 : 0;
+    if (ws_bytes < pilco_mm_bwd_workspace_bytes(gp->n, gp->D, gp->E, R, need_param)) return PILCO_ERR_WORKSPACE;
+    if (((uintptr_t)ws) & 15) return PILCO_ERR_ALIGN;
+    MMBwdParams bp = mm_bwd_params(gp, R, m, gp->D, s, (long long)gp->D * gp->D, M, gM, gS, gV,
+                                   gm, gp->D, gs, (long long)gp->D * gp->D, gX, gbeta, gell, 0, (double*)ws);
+    return mm_backward_launch(bp, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -31,10 +31,10 @@ int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
     dim3 gs(E + p.L.P, p.R);
     const int ks = ksteps_of(D);
     switch (ks) {
-        case 1: mm_setup_kernel<4><<<gs, 128, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8><<<gs, 128, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12><<<gs, 128, 0, st>>>(p); break;
-        default: mm_setup_kernel<16><<<gs, 128, 0, st>>>(p); break;
+        case 1: mm_setup_kernel<4, false><<<gs, 128, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8, false><<<gs, 128, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12, false><<<gs, 128, 0, st>>>(p); break;
+        default: mm_setup_kernel<16, false><<<gs, 128, 0, st>>>(p); break;
     }
     CUDA_LAUNCH_CHECK();
     int rc;
@@ -74,7 +74,7 @@ int pilco_mm_forward(const pilco_gp_model* gp, int R, const double* m, const dou
     if (((uintptr_t)ws) & 15) return PILCO_ERR_ALIGN;
     MMParams p;
     p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D; p.M = M; p.S = S; p.V = V; p.info = info;
-    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E);
+    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
     return mm_forward_launch(p, (cudaStream_t)stream, true);
 }
 
@@ -90,7 +90,7 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
     MMParams p;
     p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D;
     p.M = M; p.S = S; p.V = V; p.info = info;
-    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E);
+    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev[4];
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
@@ -98,10 +98,10 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
     dim3 gs(E + p.L.P, R);
     cudaEventRecord(ev[0], st);
     switch (ks) {
-        case 1: mm_setup_kernel<4><<<gs, 128, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8><<<gs, 128, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12><<<gs, 128, 0, st>>>(p); break;
-        default: mm_setup_kernel<16><<<gs, 128, 0, st>>>(p); break;
+        case 1: mm_setup_kernel<4, false><<<gs, 128, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8, false><<<gs, 128, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12, false><<<gs, 128, 0, st>>>(p); break;
+        default: mm_setup_kernel<16, false><<<gs, 128, 0, st>>>(p); break;
     }
     cudaEventRecord(ev[1], st);
     switch (ks) {

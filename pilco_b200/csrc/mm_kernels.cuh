@@ -17,9 +17,9 @@ struct MMWs {            // workspace layout, offsets in doubles relative to the
     int np, ldz, P, NB;
 };
 
-static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E) {
+static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool ordered = false) {
     MMWs L;
-    L.np = pad64(n); L.ldz = ldz_of(D); L.P = npairs_of(E); L.NB = L.np / 64;
+    L.np = pad64(n); L.ldz = ldz_of(D); L.P = ordered ? E * E : npairs_of(E); L.NB = L.np / 64;
     size_t o = 0;
     L.zeta = o;  o += (size_t)L.np * L.ldz;
     L.betap = o; o += (size_t)E * L.np;
@@ -40,6 +40,10 @@ struct MMParams {
     int* info;
     double* ws;
     MMWs L;
+    // backward-mode setup (ordered pairs q = a*E + b): also store Q_ab, C_ab=(s+diag(1/delta))^-1 and
+    // logdet R_ab per pair; offsets (doubles, per restart) of those arrays inside ws.  bwd==0: unused.
+    int bwd;
+    size_t oQ, oC, oLd;
 };
 
 #define TILE_CM 512        // columns staged in shared memory per chunk
@@ -58,9 +62,9 @@ __device__ __forceinline__ void load_sym_s(const double* __restrict__ s, int D, 
     }
 }
 
-template <int DP>
+template <int DP, bool BWD>
 __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
-    const int r = blockIdx.y, task = blockIdx.x;
+    const int r = blockIdx.y, task = BWD ? blockIdx.x + p.gp.E : blockIdx.x;   // BWD: pair tasks only
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
     const MMWs& L = p.L;
@@ -70,6 +74,7 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
     __shared__ double s_s[MAXD * SLD];      // symmetrised input covariance
     __shared__ double sA[MAXD * SLD];       // matrix being factored
     __shared__ double sB[MAXD * SLD];       // W_a or Q_ab
+    __shared__ double sC[BWD ? MAXD * SLD : 1];   // BWD: (s + diag(1/delta))^-1
     __shared__ double sinvd[MAXD];
     __shared__ double sm[MAXD], spa[MAXD], spb[MAXD], sdinv[MAXD];
     __shared__ double sred[(MAXD + 1) * 4], sout[MAXD + 1];
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
     if (tid < DP) sm[tid] = tid < D ? mr[tid] : 0.0;
     __syncthreads();
 
-    if (task < E) {
+    if (!BWD && task < E) {
         // ---------------- output task: mean and input-output covariance of GP a ----------------
         const int a = task;
         if (tid < DP) { const double l = tid < D ? ell[a * D + tid] : 1.0; spa[tid] = l * l; }
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
     // ---------------- pair task (a <= b): Q_ab and the per-centre exponent pieces ----------------
     const int q = task - E;
     int a, b;
-    pair_decode(q, a, b);
+    if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);
     if (tid < DP) {
         const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
         spa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
@@ -167,11 +172,13 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
         const double dd = (i < D) ? sdinv[i] : 1.0;
         sA[i * SLD + j] = s_s[i * SLD + j] + (i == j ? dd : 0.0);
         sB[i * SLD + j] = s_s[i * SLD + j];
+        if (BWD) sC[i * SLD + j] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
     if (warp == 0) {
         const bool ok = chol_warp(sA, sinvd, DP, lane);
         chol_solve_warp(sA, sinvd, sB, DP, DP, lane);            // sB = (s + Dd^-1)^-1 s
+        if (BWD) chol_solve_warp(sA, sinvd, sC, DP, DP, lane);   // sC = (s + Dd^-1)^-1
         if (lane == 0) {
             double ld = chol_logdet(sinvd, DP);
             for (int d = 0; d < D; ++d) ld += log(spa[d] + spb[d]);
@@ -189,6 +196,16 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
         sA[i * SLD + j] = 0.25 * (qi + qj);
     }
     __syncthreads();
+    if (BWD) {
+        double* Qo = wsr + p.oQ + (size_t)q * D * D;
+        double* Co = wsr + p.oC + (size_t)q * D * D;
+        for (int e = tid; e < D * D; e += blockDim.x) {
+            const int i = e / D, j = e % D;
+            Qo[e] = sA[i * SLD + j];
+            Co[e] = 0.5 * (sC[i * SLD + j] + sC[j * SLD + i]);
+        }
+        if (tid == 0) wsr[p.oLd + q] = slogdet;
+    }
     const double lsa = log(sf2[a]), lsb = log(sf2[b]);
     const double hld = 0.5 * slogdet;
     for (int nn = tid; nn < np; nn += blockDim.x) {
@@ -222,6 +239,13 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
             }
             Apv = ka + qa - hld;
             Bqv = kb + qb;
+        }
+        if (BWD) {
+            if (b == 0) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
+            if (q == 0) {
+                for (int d = 0; d < ldz; ++d)
+                    wsr[L.zeta + (size_t)nn * ldz + d] = (nn < n && d < D) ? X[(size_t)nn * D + d] - sm[d] : 0.0;
+            }
         }
         wsr[L.Ap + (size_t)q * np + nn] = Apv;
         wsr[L.Bq + (size_t)q * np + nn] = Bqv;

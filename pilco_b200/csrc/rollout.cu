@@ -7,29 +7,8 @@
 //   (RBF policy)  mm_setup/mm_tile on the policy GP, then ro_policy<t>: finish + squash + joint
 //   mm_setup / mm_tile on the dynamics GP with the joint Gaussian of step t
 // and a final ro_state<H> that closes the last step.
-#include "mm_kernels.cuh"
+#include "rollout.cuh"
 #include "small_kernels.cuh"
-
-struct RoWs {                 // offsets in doubles
-    size_t mj, sj, Md, Sd, Vd, Mp, Sp, Vp, Mu, Su, Cq, Vu, dynws, polws, total;
-};
-
-static RoWs ro_ws_layout(const pilco_rollout* ro) {
-    const size_t R = ro->R, H = ro->H;
-    const size_t Ds = ro->pol.Ds, U = ro->pol.U, D = Ds + U, E = Ds;
-    RoWs L; size_t o = 0;
-    auto take = [&](size_t len) { size_t at = o; o += (H * R * len + 1) & ~(size_t)1; return at; };
-    L.mj = take(D); L.sj = take(D * D);
-    L.Md = take(E); L.Sd = take(E * E); L.Vd = take(D * E);
-    L.Mp = take(U); L.Sp = take(U * U); L.Vp = take(Ds * U);
-    L.Mu = take(U); L.Su = take(U * U); L.Cq = take(U * U); L.Vu = take(Ds * U);
-    L.dynws = o; o += pilco_mm_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R) / 8;
-    L.polws = o;
-    if (ro->pol.kind == PILCO_POLICY_RBF)
-        o += pilco_mm_workspace_bytes(ro->pol.rbf.n, ro->pol.rbf.D, ro->pol.rbf.E, ro->R) / 8;
-    L.total = o;
-    return L;
-}
 
 struct RoDev {
     int R, H, Ds, U, t;
@@ -122,7 +101,7 @@ __global__ void __launch_bounds__(128) ro_policy_kernel(RoDev p) {
     ro_action_tail(p, r, mx, sx, sc);
 }
 
-static int ro_check(const pilco_rollout* ro) {
+int ro_check(const pilco_rollout* ro) {
     if (!ro) return PILCO_ERR_NULL;
     if (ro->R < 1 || ro->H < 0) return PILCO_ERR_DIM;
     int rc = mm_check_model(&ro->dyn);
@@ -179,7 +158,7 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
         p.gp = ro->dyn; p.R = R;
         p.m = slot(L.mj, D, t); p.s = slot(L.sj, (size_t)D * D, t); p.m_rs = D; p.s_rs = (long long)D * D;
         p.M = slot(L.Md, Ds, t); p.S = slot(L.Sd, (size_t)Ds * Ds, t); p.V = slot(L.Vd, (size_t)D * Ds, t);
-        p.info = ro->info; p.ws = ws + L.dynws; p.L = mm_ws_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E);
+        p.info = ro->info; p.ws = ws + L.dynws; p.L = mm_ws_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
         return p;
     };
     auto pol_params = [&](int t) {
@@ -188,7 +167,7 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
         p.m = ro->traj_m + (size_t)t * Ds; p.s = ro->traj_S + (size_t)t * Ds * Ds;
         p.m_rs = (long long)(H + 1) * Ds; p.s_rs = (long long)(H + 1) * Ds * Ds;
         p.M = slot(L.Mp, U, t); p.S = slot(L.Sp, (size_t)U * U, t); p.V = slot(L.Vp, (size_t)Ds * U, t);
-        p.info = ro->info; p.ws = ws + L.polws; p.L = mm_ws_layout(ro->pol.rbf.n, ro->pol.rbf.D, ro->pol.rbf.E);
+        p.info = ro->info; p.ws = ws + L.polws; p.L = mm_ws_layout(ro->pol.rbf.n, ro->pol.rbf.D, ro->pol.rbf.E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
         return p;
     };
 

@@ -1,0 +1,286 @@
+// rollout_bwd.cu -- reverse sweep of the H-step cascade: d(sum_t E[r(x_t)]) / d(policy parameters).
+// The reference obtains this gradient from TensorFlow autodiff through tf.while_loop
+// (pilco/models/pilco.py:47-50, 84-90); here every stage has a hand-derived VJP (oracle/staged.py) and the
+// forward's per-step joint Gaussians / policy moments saved by pilco_rollout_forward are re-used, while the
+// N x N exponentials are recomputed tile-wise (never stored).
+//
+// Per step t = H-1 .. 0:
+//   rb_pre   grid R : glue VJP -> seeds (gMd, gSd, gVd) of the dynamics moment match, extra d/d(joint cov)
+//   mm_backward (dynamics GP) -> g(joint mean), g(joint cov)
+//   rb_post  grid R : joint VJP, squash VJP, [linear policy VJP], reward VJP -> state cotangent (gm_t, gS_t),
+//                     seeds (gMp, gSp, gVp) of the policy moment match
+//   mm_backward (RBF policy GP, accumulating) -> adds to (gm_t, gS_t) and to g(centres), g(beta), g(lengthscales)
+// then, for the RBF policy, the VJP through beta = (K + sn2 I)^-1 Y.
+#include "mm_backward.cuh"
+#include "rollout.cuh"
+#include "small_kernels.cuh"
+
+extern "C" size_t pilco_mm_bwd_workspace_bytes(int n, int D, int E, int R, int need_param);
+void chol_solve_vec_launch(cudaStream_t st, int batch, int n, const double* L, int ld, long long ms, int E,
+                           const double* Y, long long Y_bs, long long y_es, int yinc, double* x, long long xs);
+
+struct RbWs {            // backward workspace (offsets in doubles)
+    size_t gm, gS, gMd, gSd, gVd, gmj, gsj, gsjx, gMp, gSp, gVp, gbeta, gy, dynb, polb, total;
+};
+
+static RbWs rb_ws_layout(const pilco_rollout* ro) {
+    const size_t R = ro->R, Ds = ro->pol.Ds, U = ro->pol.U, D = Ds + U;
+    RbWs L; size_t o = 0;
+    auto take = [&](size_t len) { size_t at = o; o += (R * len + 1) & ~(size_t)1; return at; };
+    L.gm = take(Ds); L.gS = take(Ds * Ds);
+    L.gMd = take(Ds); L.gSd = take(Ds * Ds); L.gVd = take(D * Ds);
+    L.gmj = take(D); L.gsj = take(D * D); L.gsjx = take(D * D);
+    L.gMp = take(U); L.gSp = take(U * U); L.gVp = take(Ds * U);
+    const size_t bf = ro->pol.kind == PILCO_POLICY_RBF ? ro->pol.rbf.n : 0;
+    L.gbeta = take(U * bf); L.gy = take(U * bf);
+    L.dynb = o; o += pilco_mm_bwd_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R, 0) / 8;
+    L.polb = o;
+    if (ro->pol.kind == PILCO_POLICY_RBF)
+        o += pilco_mm_bwd_workspace_bytes(ro->pol.rbf.n, ro->pol.rbf.D, ro->pol.rbf.E, ro->R, 1) / 8;
+    L.total = o;
+    return L;
+}
+
+struct RbDev {
+    int R, H, Ds, U, t;
+    int pol_kind, squash;
+    const double* maxa;
+    const double* W; long long W_bs;
+    int n_rewards; pilco_reward_term rewards[8];
+    const double* traj_m; const double* traj_S;
+    // forward slots of step t
+    const double *sj, *Vd, *Mp, *Sp, *Vp, *Mu, *Su, *Cq, *Vu;
+    // cotangent buffers [R, len]
+    double *gm, *gS, *gMd, *gSd, *gVd, *gmj, *gsj, *gsjx, *gMp, *gSp, *gVp;
+    double *gW, *gb;      // linear policy gradient accumulators [R,U,Ds], [R,U]
+};
+
+__global__ void __launch_bounds__(128) rb_pre_kernel(RbDev p) {
+    const int r = blockIdx.x, Ds = p.Ds, U = p.U, D = Ds + U;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double* gm = p.gm + (size_t)r * Ds;
+    const double* gS = p.gS + (size_t)r * Ds * Ds;
+    const double* sj = p.sj + (size_t)r * D * D;
+    const double* Vd = p.Vd + (size_t)r * D * Ds;
+    for (int i = tid; i < Ds; i += nt) p.gMd[(size_t)r * Ds + i] = gm[i];
+    for (int e = tid; e < Ds * Ds; e += nt) p.gSd[(size_t)r * Ds * Ds + e] = gS[e];
+    // gVd = s1^T (gS + gS^T),   s1 = sj[:Ds, :]
+    for (int e = tid; e < D * Ds; e += nt) {
+        const int k = e / Ds, j = e % Ds;
+        double v = 0.0;
+        for (int i = 0; i < Ds; ++i) v = fma(sj[i * D + k], gS[i * Ds + j] + gS[j * Ds + i], v);
+        p.gVd[(size_t)r * D * Ds + e] = v;
+    }
+    // extra cotangent of the joint covariance: rows < Ds get (gS + gS^T) Vd^T
+    for (int e = tid; e < D * D; e += nt) {
+        const int i = e / D, k = e % D;
+        double v = 0.0;
+        if (i < Ds) for (int j = 0; j < Ds; ++j) v = fma(gS[i * Ds + j] + gS[j * Ds + i], Vd[k * Ds + j], v);
+        p.gsjx[(size_t)r * D * D + e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
+    __shared__ SmallScratch sc;
+    __shared__ double gMu[MAXD], gSu[MAXD * MAXD], gVu[MAXD * MAXD], gB[MAXD * MAXD], gCd[MAXD];
+    const int r = blockIdx.x, Ds = p.Ds, U = p.U, D = Ds + U, t = p.t;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double* gm = p.gm + (size_t)r * Ds;
+    double* gS = p.gS + (size_t)r * Ds * Ds;
+    const double* gmj = p.gmj + (size_t)r * D;
+    const double* gsj = p.gsj + (size_t)r * D * D;
+    const double* gsjx = p.gsjx + (size_t)r * D * D;
+    const double* mx = p.traj_m + ((size_t)r * (p.H + 1) + t) * Ds;
+    const double* sx = p.traj_S + ((size_t)r * (p.H + 1) + t) * Ds * Ds;
+    const double* Vu = p.Vu + (size_t)r * Ds * U;
+    const double* Vp = p.Vp + (size_t)r * Ds * U;
+    const double* Cq = p.Cq + (size_t)r * U * U;
+    // ---- joint VJP (pilco.py:141-144) ----
+    for (int e = tid; e < Ds * U; e += nt) {                 // gB = G12 + G21^T
+        const int i = e / U, j = e % U;
+        gB[e] = gsj[i * D + Ds + j] + gsjx[i * D + Ds + j] + gsj[(Ds + j) * D + i] + gsjx[(Ds + j) * D + i];
+    }
+    for (int i = tid; i < U; i += nt) gMu[i] = gmj[Ds + i];
+    for (int e = tid; e < U * U; e += nt) {
+        const int i = e / U, j = e % U;
+        gSu[e] = gsj[(Ds + i) * D + Ds + j] + gsjx[(Ds + i) * D + Ds + j];
+    }
+    __syncthreads();
+    for (int i = tid; i < Ds; i += nt) gm[i] += gmj[i];
+    for (int e = tid; e < Ds * Ds; e += nt) {
+        const int i = e / Ds, j = e % Ds;
+        double v = gsj[i * D + j] + gsjx[i * D + j];
+        for (int k = 0; k < U; ++k) v = fma(gB[i * U + k], Vu[j * U + k], v);       // gB Vu^T
+        gS[e] += v;
+    }
+    for (int e = tid; e < Ds * U; e += nt) {                 // gVu = s_x^T gB
+        const int i = e / U, j = e % U;
+        double v = 0.0;
+        for (int k = 0; k < Ds; ++k) v = fma(sx[k * Ds + i], gB[k * U + j], v);
+        gVu[e] = v;
+    }
+    __syncthreads();
+    // ---- squash VJP (controllers.py:13-36, 118-120):  Vu = Vp C ----
+    double* gMp = p.gMp + (size_t)r * U;
+    double* gSp = p.gSp + (size_t)r * U * U;
+    double* gVp = p.gVp + (size_t)r * Ds * U;
+    if (p.squash) {
+        for (int k = tid; k < U; k += nt) {
+            double v = 0.0;
+            for (int i = 0; i < Ds; ++i) v = fma(Vp[i * U + k], gVu[i * U + k], v);
+            gCd[k] = v;
+        }
+        for (int e = tid; e < Ds * U; e += nt) gVp[e] = gVu[e] * Cq[(e % U) * U + (e % U)];
+        __syncthreads();
+        dev_squash_bwd(U, p.Mp + (size_t)r * U, p.Sp + (size_t)r * U * U, p.maxa,
+                       p.Mu + (size_t)r * U, p.Su + (size_t)r * U * U, gMu, gSu, gCd, gMp, gSp);
+    } else {
+        for (int i = tid; i < U; i += nt) gMp[i] = gMu[i];
+        for (int e = tid; e < U * U; e += nt) gSp[e] = gSu[e];
+        for (int e = tid; e < Ds * U; e += nt) gVp[e] = gVu[e];
+        __syncthreads();
+    }
+    // ---- linear policy VJP (controllers.py:52-54) ----
+    if (p.pol_kind == PILCO_POLICY_LINEAR) {
+        dev_linear_bwd(Ds, U, p.W + (size_t)r * p.W_bs, mx, sx, gMp, gSp, gVp,
+                       p.gW + (size_t)r * U * Ds, p.gb + (size_t)r * U, gm, gS, sc);
+    }
+    // ---- reward VJP at state t (pilco.py:133) ----
+    for (int k = 0; k < p.n_rewards; ++k) {
+        const pilco_reward_term& rt = p.rewards[k];
+        if (rt.kind == PILCO_REWARD_EXP) dev_exp_reward_bwd(Ds, rt.W, rt.t, mx, sx, rt.coef, gm, gS, sc);
+        else { for (int i = tid; i < Ds; i += nt) gm[i] += rt.coef * rt.W[i]; __syncthreads(); }
+    }
+}
+
+// VJP through beta_a = (K_a + sn2 I)^-1 y_a for the RBF policy (sf2 = 1): given gy_a = (K_a+sn2 I)^-1 gbeta_a,
+//   gY[:,a] = gy_a ;  gK = -gy beta^T ;  gX += ..., gell += ...   (oracle/staged.py: rbf_factor_backward)
+__global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int U, const double* X, const double* ell,
+                                                             const double* beta, const double* gy,
+                                                             double* gX, double* gY, double* gell) {
+    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const double* Xr = X + (size_t)r * bf * Ds;
+    const double* lr = ell + (size_t)r * U * Ds;
+    const double* br = beta + (size_t)r * U * bf;
+    const double* gr = gy + (size_t)r * U * bf;
+    for (int e = tid; e < bf * U; e += nt) { const int n = e / U, a = e % U; gY[(size_t)r * bf * U + e] = gr[a * bf + n]; }
+    for (int e = tid; e < bf * Ds; e += nt) {
+        const int n = e / Ds, d = e % Ds;
+        double acc = 0.0;
+        for (int a = 0; a < U; ++a) {
+            const double il2 = 1.0 / (lr[a * Ds + d] * lr[a * Ds + d]);
+            for (int m = 0; m < bf; ++m) {
+                double d2 = 0.0;
+                for (int k = 0; k < Ds; ++k) { const double tt = (Xr[n * Ds + k] - Xr[m * Ds + k]) / lr[a * Ds + k]; d2 = fma(tt, tt, d2); }
+                const double K = exp(-0.5 * d2);
+                const double P = -(gr[a * bf + n] * br[a * bf + m] + gr[a * bf + m] * br[a * bf + n]) * K;
+                acc = fma(-P * il2, Xr[n * Ds + d] - Xr[m * Ds + d], acc);
+            }
+        }
+        gX[(size_t)r * bf * Ds + e] += acc;
+    }
+    for (int e = tid; e < U * Ds; e += nt) {
+        const int a = e / Ds, d = e % Ds;
+        double acc = 0.0;
+        for (int n = 0; n < bf; ++n)
+            for (int m = 0; m < bf; ++m) {
+                double d2 = 0.0;
+                for (int k = 0; k < Ds; ++k) { const double tt = (Xr[n * Ds + k] - Xr[m * Ds + k]) / lr[a * Ds + k]; d2 = fma(tt, tt, d2); }
+                const double diff = Xr[n * Ds + d] - Xr[m * Ds + d];
+                acc = fma(-gr[a * bf + n] * br[a * bf + m] * exp(-0.5 * d2), diff * diff, acc);
+            }
+        const double l = lr[a * Ds + d];
+        gell[(size_t)r * U * Ds + e] += acc / (l * l * l);
+    }
+}
+
+extern "C" {
+
+size_t pilco_rollout_bwd_workspace_bytes(const pilco_rollout* ro) {
+    if (!ro || ro->R < 1 || ro->H < 0) return 0;
+    return rb_ws_layout(ro).total * sizeof(double);
+}
+
+int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g, pilco_stream_t stream) {
+    int rc = ro_check(ro);
+    if (rc) return rc;
+    if (!g || !g->ws) return PILCO_ERR_NULL;
+    const RoWs FL = ro_ws_layout(ro);
+    const RbWs BL = rb_ws_layout(ro);
+    if (g->ws_bytes < BL.total * sizeof(double)) return PILCO_ERR_WORKSPACE;
+    if (((uintptr_t)g->ws) & 15) return PILCO_ERR_ALIGN;
+    const int R = ro->R, H = ro->H, Ds = ro->pol.Ds, U = ro->pol.U, D = Ds + U;
+    const bool rbf = ro->pol.kind == PILCO_POLICY_RBF;
+    if (rbf) { if (!g->gXc || !g->gYc || !g->gell || !g->pol_L) return PILCO_ERR_NULL; }
+    else { if (!g->gW || !g->gb) return PILCO_ERR_NULL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* fws = (double*)ro->ws;
+    double* bws = (double*)g->ws;
+    const size_t RR = (size_t)R;
+    auto slot = [&](size_t base, size_t len, int t) { return fws + base + (size_t)t * RR * len; };
+    auto buf = [&](size_t base) { return bws + base; };
+
+    // zero the state cotangent and the parameter-gradient accumulators
+    cudaMemsetAsync(buf(BL.gm), 0, sizeof(double) * ((BL.gMd - BL.gm)), st);
+    const int bf = rbf ? ro->pol.rbf.n : 0;
+    if (rbf) {
+        cudaMemsetAsync(g->gXc, 0, sizeof(double) * RR * bf * Ds, st);
+        cudaMemsetAsync(g->gell, 0, sizeof(double) * RR * U * Ds, st);
+        cudaMemsetAsync(buf(BL.gbeta), 0, sizeof(double) * RR * U * bf, st);
+    } else {
+        cudaMemsetAsync(g->gW, 0, sizeof(double) * RR * U * Ds, st);
+        cudaMemsetAsync(g->gb, 0, sizeof(double) * RR * U, st);
+    }
+
+    RbDev d;
+    d.R = R; d.H = H; d.Ds = Ds; d.U = U;
+    d.pol_kind = ro->pol.kind; d.squash = ro->pol.squash; d.maxa = ro->pol.max_action;
+    d.W = ro->pol.W; d.W_bs = ro->pol.W_bs;
+    d.n_rewards = ro->n_rewards;
+    for (int k = 0; k < 8; ++k) d.rewards[k] = ro->rewards[k];
+    d.traj_m = ro->traj_m; d.traj_S = ro->traj_S;
+    d.gm = buf(BL.gm); d.gS = buf(BL.gS); d.gMd = buf(BL.gMd); d.gSd = buf(BL.gSd); d.gVd = buf(BL.gVd);
+    d.gmj = buf(BL.gmj); d.gsj = buf(BL.gsj); d.gsjx = buf(BL.gsjx);
+    d.gMp = buf(BL.gMp); d.gSp = buf(BL.gSp); d.gVp = buf(BL.gVp);
+    d.gW = g->gW; d.gb = g->gb;
+
+    for (int t = H - 1; t >= 0; --t) {
+        d.t = t;
+        d.sj = slot(FL.sj, (size_t)D * D, t); d.Vd = slot(FL.Vd, (size_t)D * Ds, t);
+        d.Mp = slot(FL.Mp, U, t); d.Sp = slot(FL.Sp, (size_t)U * U, t); d.Vp = slot(FL.Vp, (size_t)Ds * U, t);
+        d.Mu = slot(FL.Mu, U, t); d.Su = slot(FL.Su, (size_t)U * U, t); d.Cq = slot(FL.Cq, (size_t)U * U, t);
+        d.Vu = slot(FL.Vu, (size_t)Ds * U, t);
+        rb_pre_kernel<<<R, 128, 0, st>>>(d);
+        CUDA_LAUNCH_CHECK();
+        MMBwdParams bp = mm_bwd_params(&ro->dyn, R, slot(FL.mj, D, t), D, slot(FL.sj, (size_t)D * D, t), (long long)D * D,
+                                       slot(FL.Md, Ds, t), d.gMd, d.gSd, d.gVd,
+                                       d.gmj, D, d.gsj, (long long)D * D, nullptr, nullptr, nullptr, 0, bws + BL.dynb);
+        rc = mm_backward_launch(bp, st);
+        if (rc) return rc;
+        rb_post_kernel<<<R, 128, 0, st>>>(d);
+        CUDA_LAUNCH_CHECK();
+        if (rbf) {
+            MMBwdParams pp = mm_bwd_params(&ro->pol.rbf, R, ro->traj_m + (size_t)t * Ds, (long long)(H + 1) * Ds,
+                                           ro->traj_S + (size_t)t * Ds * Ds, (long long)(H + 1) * Ds * Ds,
+                                           slot(FL.Mp, U, t), d.gMp, d.gSp, d.gVp,
+                                           d.gm, Ds, d.gS, (long long)Ds * Ds,
+                                           g->gXc, buf(BL.gbeta), g->gell, 1, bws + BL.polb);
+            rc = mm_backward_launch(pp, st);
+            if (rc) return rc;
+        }
+    }
+    if (rbf) {
+        // gy = (K + sn2 I)^-1 gbeta  with the Cholesky factors kept by pilco_gp_factorize
+        const int ldw = pad64(bf);
+        chol_solve_vec_launch(st, R * U, bf, g->pol_L, ldw, (long long)ldw * ldw, U,
+                              buf(BL.gbeta), (long long)U * bf, bf, 1, buf(BL.gy), bf);
+        rbf_factor_bwd_kernel<<<R, 128, 0, st>>>(bf, Ds, U, ro->pol.rbf.X, ro->pol.rbf.ell, ro->pol.rbf.beta,
+                                                  buf(BL.gy), g->gXc, g->gYc, g->gell);
+        CUDA_LAUNCH_CHECK();
+    }
+    if (g->gm0) cudaMemcpyAsync(g->gm0, d.gm, sizeof(double) * RR * Ds, cudaMemcpyDeviceToDevice, st);
+    if (g->gS0) cudaMemcpyAsync(g->gS0, d.gS, sizeof(double) * RR * Ds * Ds, cudaMemcpyDeviceToDevice, st);
+    return PILCO_OK;
+}
+
+}  // extern "C"

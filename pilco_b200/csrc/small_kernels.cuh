@@ -164,4 +164,128 @@ __device__ __forceinline__ double dev_linear_reward(int Ds, const double* W, con
     return mu;
 }
 
+// ---------------------------------------------------------------------------------------------
+// VJPs (numpy statement: oracle/staged.py).  All "g*" outputs marked += accumulate.
+// ---------------------------------------------------------------------------------------------
+// squash_sin VJP.  m,s: pre-squash moments; Mu,Su: squashed outputs; gM,gS,gCd: upstream cotangents of
+// (M, S, diag C).  Writes gm[U], gs[U,U].
+__device__ __forceinline__ void dev_squash_bwd(int U, const double* m, const double* s, const double* maxa,
+                                               const double* Mu, const double* Su,
+                                               const double* gM, const double* gS, const double* gCd,
+                                               double* gm, double* gs) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < U * U; e += nt) {
+        const int i = e / U, j = e % U;
+        const double lq = -0.5 * (s[i * U + i] + s[j * U + j]);
+        const double E1 = exp(lq + s[e]), E2 = exp(lq - s[e]);
+        gs[e] = gS[e] * 0.5 * maxa[i] * maxa[j] * (E1 * cos(m[i] - m[j]) + E2 * cos(m[i] + m[j]));
+    }
+    __syncthreads();
+    for (int i = tid; i < U; i += nt) {
+        const double ci = maxa[i] * exp(-0.5 * s[i * U + i]) * cos(m[i]);
+        double gmi = gM[i] * ci - gCd[i] * Mu[i];
+        double gd = -0.5 * gM[i] * Mu[i] - 0.5 * gCd[i] * ci;
+        for (int j = 0; j < U; ++j) {
+            const double lq = -0.5 * (s[i * U + i] + s[j * U + j]);
+            const double q = exp(lq);
+            const double f = 0.5 * maxa[i] * maxa[j];
+            const double sij = s[i * U + j], sji = s[j * U + i];
+            // pair (i,j): derivative w.r.t. m_i (first index)
+            gmi += gS[i * U + j] * f * (-(exp(lq + sij) - q) * sin(m[i] - m[j]) + (exp(lq - sij) - q) * sin(m[i] + m[j]));
+            // pair (j,i): derivative w.r.t. m_i (second index)
+            gmi += gS[j * U + i] * f * ((exp(lq + sji) - q) * sin(m[j] - m[i]) + (exp(lq - sji) - q) * sin(m[j] + m[i]));
+            gd += -0.5 * (gS[i * U + j] * Su[i * U + j] + gS[j * U + i] * Su[j * U + i]);
+        }
+        gm[i] = gmi;
+        gs[i * U + i] += gd;
+    }
+    __syncthreads();
+}
+
+// ExponentialReward VJP (reward.m:48-49, W symmetric):  gm += scale dmu/dm,  gS += scale dmu/dS
+__device__ __forceinline__ void dev_exp_reward_bwd(int Ds, const double* W, const double* t, const double* m,
+                                                   const double* s, double scale, double* gm, double* gS,
+                                                   SmallScratch& sc) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();
+    for (int e = tid; e < Ds * Ds; e += nt) {
+        const int i = e / Ds, j = e % Ds;
+        double v = 0.0;
+        for (int k = 0; k < Ds; ++k) v = fma(s[i * Ds + k], W[k * Ds + j], v);
+        sc.A[i * SLD + j] = v + (i == j ? 1.0 : 0.0);
+        sc.B[i * SLD + j] = (i == j) ? 1.0 : 0.0;
+    }
+    for (int i = tid; i < Ds; i += nt) sc.v[i] = m[i] - t[i];
+    __syncthreads();
+    if (warp == 0) {
+        double det;
+        lu_warp(sc.A, sc.perm, Ds, lane, &det);
+        lu_solve_warp(sc.A, sc.perm, sc.B, sc.C, Ds, Ds, lane);          // C = (I + sW)^-1
+        if (lane == 0) sc.det = det;
+    }
+    __syncthreads();
+    for (int e = tid; e < Ds * Ds; e += nt) {                            // B = iSpW = W (I+sW)^-1
+        const int i = e / Ds, j = e % Ds;
+        double v = 0.0;
+        for (int k = 0; k < Ds; ++k) v = fma(W[i * Ds + k], sc.C[k * SLD + j], v);
+        sc.B[i * SLD + j] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < Ds; i += nt) {
+        double v = 0.0;
+        for (int k = 0; k < Ds; ++k) v = fma(sc.B[i * SLD + k], sc.v[k], v);
+        sc.w[i] = v;                                                     // wy = iSpW (m-t)
+    }
+    __syncthreads();
+    double quad = 0.0;
+    for (int i = 0; i < Ds; ++i) quad = fma(sc.v[i], sc.w[i], quad);
+    const double mu = exp(-0.5 * quad) / sqrt(sc.det);
+    for (int i = tid; i < Ds; i += nt) gm[i] += -scale * mu * sc.w[i];
+    for (int e = tid; e < Ds * Ds; e += nt) {
+        const int i = e / Ds, j = e % Ds;
+        const double isym = 0.5 * (sc.B[i * SLD + j] + sc.B[j * SLD + i]);
+        gS[e] += 0.5 * scale * mu * (sc.w[i] * sc.w[j] - isym);
+    }
+    __syncthreads();
+}
+
+// LinearController VJP: gW += gMp m^T + (gSp+gSp^T) W s + gVp^T ; gb += gMp ; gm += W^T gMp ; gS += W^T gSp W
+__device__ __forceinline__ void dev_linear_bwd(int Ds, int U, const double* W, const double* m, const double* s,
+                                               const double* gMp, const double* gSp, const double* gVp,
+                                               double* gW, double* gb, double* gm, double* gS, SmallScratch& sc) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int e = tid; e < U * Ds; e += nt) {                 // A = W s  [U,Ds]
+        const int i = e / Ds, k = e % Ds;
+        double v = 0.0;
+        for (int l = 0; l < Ds; ++l) v = fma(W[i * Ds + l], 0.5 * (s[l * Ds + k] + s[k * Ds + l]), v);
+        sc.A[i * SLD + k] = v;
+    }
+    for (int e = tid; e < U * Ds; e += nt) {                 // B = gSp W  [U,Ds]
+        const int i = e / Ds, k = e % Ds;
+        double v = 0.0;
+        for (int j = 0; j < U; ++j) v = fma(gSp[i * U + j], W[j * Ds + k], v);
+        sc.B[i * SLD + k] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < U * Ds; e += nt) {
+        const int i = e / Ds, k = e % Ds;
+        double v = gMp[i] * m[k] + gVp[k * U + i];
+        for (int j = 0; j < U; ++j) v = fma(gSp[i * U + j] + gSp[j * U + i], sc.A[j * SLD + k], v);
+        gW[e] += v;
+    }
+    for (int i = tid; i < U; i += nt) gb[i] += gMp[i];
+    for (int k = tid; k < Ds; k += nt) {
+        double v = 0.0;
+        for (int i = 0; i < U; ++i) v = fma(W[i * Ds + k], gMp[i], v);
+        gm[k] += v;
+    }
+    for (int e = tid; e < Ds * Ds; e += nt) {
+        const int k = e / Ds, l = e % Ds;
+        double v = 0.0;
+        for (int i = 0; i < U; ++i) v = fma(W[i * Ds + k], sc.B[i * SLD + l], v);
+        gS[e] += v;
+    }
+    __syncthreads();
+}
+
 #endif  // __CUDACC__

@@ -89,7 +89,20 @@ def gp_factorize(X, Y, ell, sf2, sn2, need_iK=True, mode=0):
           "gp_factorize")
     gp = DeviceGP(X, ell, sf2, beta, iK, ldk, mode=mode, batched=batched)
     gp.info = info
+    gp.fact_ws = ws            # first B*E*ldw*ldw doubles = Cholesky factors (needed by the policy VJP)
+    gp.Y, gp.sn2 = Y, sn2
     return gp
+
+
+def gp_refactorize(gp):
+    """Re-run pilco_gp_factorize in place after gp.X / gp.Y / gp.ell were overwritten (policy optimisation)."""
+    B = gp.X.shape[0] if gp.batched else 1
+    n, D, E = gp.n, gp.D, gp.E
+    bs = lambda per: (per if gp.batched else 0)
+    wsb = gp.fact_ws.numel() * 8
+    check(lib.pilco_gp_factorize(n, D, E, B, ptr(gp.X), bs(n * D), ptr(gp.Y), bs(n * E), ptr(gp.ell), bs(E * D),
+                                 ptr(gp.sf2), bs(E), ptr(gp.sn2), bs(E), ptr(gp.iK), gp.ldk, ptr(gp.beta),
+                                 ptr(gp.info), ptr(gp.fact_ws), wsb, stream_ptr()), "gp_factorize")
 
 
 def fitc_factorize(X, Z, Y, ell, sf2, sn2):
@@ -128,6 +141,26 @@ def mm_forward(gp, m, s):
     check(lib.pilco_mm_forward(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(S), ptr(V), ptr(info),
                                ptr(ws), wsb, stream_ptr()), "mm_forward")
     return M, S, V, info
+
+
+def mm_backward(gp, m, s, M, gM, gS, gV, need_param=False):
+    """pilco_mm_backward -> gm [R,D], gs [R,D,D] (+ gX [R,n,D], gbeta [R,E,n], gell [R,E,D])."""
+    m, s, M, gM, gS, gV = dev(m), dev(s), dev(M), dev(gM), dev(gS), dev(gV)
+    R = m.shape[0]
+    d = device()
+    gm = torch.empty((R, gp.D), dtype=F64, device=d)
+    gs = torch.empty((R, gp.D, gp.D), dtype=F64, device=d)
+    gX = gb = gl = None
+    if need_param:
+        gX = torch.empty((R, gp.n, gp.D), dtype=F64, device=d)
+        gb = torch.empty((R, gp.E, gp.n), dtype=F64, device=d)
+        gl = torch.empty((R, gp.E, gp.D), dtype=F64, device=d)
+    wsb = lib.pilco_mm_bwd_workspace_bytes(gp.n, gp.D, gp.E, R, 1 if need_param else 0)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    g = gp.struct()
+    check(lib.pilco_mm_backward(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(gM), ptr(gS), ptr(gV),
+                                ptr(gm), ptr(gs), ptr(gX), ptr(gb), ptr(gl), ptr(ws), wsb, stream_ptr()), "mm_backward")
+    return gm, gs, gX, gb, gl
 
 
 def squash_sin(m, s, max_action):
@@ -223,3 +256,32 @@ class RolloutPlan:
     def forward(self):
         check(lib.pilco_rollout_forward(C.byref(self.ro), stream_ptr()), "rollout_forward")
         return self.traj_m, self.traj_S, self.reward
+
+    def backward(self):
+        """pilco_rollout_backward: d reward[r] / d policy parameters (call after forward()).
+        Linear: {'W': [R,U,Ds], 'b': [R,U]};  RBF: {'X': [R,bf,Ds], 'Y': [R,bf,U], 'ell': [R,U,Ds]}."""
+        d = device()
+        if not hasattr(self, "grad"):
+            g = _lib.RolloutGrad()
+            R, Ds, U = self.R, self.Ds, self.U
+            self.gbuf = {}
+            if self.ro.pol.kind == _lib.POLICY_LINEAR:
+                self.gbuf["W"] = torch.empty((R, U, Ds), dtype=F64, device=d)
+                self.gbuf["b"] = torch.empty((R, U), dtype=F64, device=d)
+                g.gW, g.gb = self.gbuf["W"].data_ptr(), self.gbuf["b"].data_ptr()
+            else:
+                bf = self.rbf.n
+                self.gbuf["X"] = torch.empty((R, bf, Ds), dtype=F64, device=d)
+                self.gbuf["Y"] = torch.empty((R, bf, U), dtype=F64, device=d)
+                self.gbuf["ell"] = torch.empty((R, U, Ds), dtype=F64, device=d)
+                g.gXc, g.gYc, g.gell = (self.gbuf[k].data_ptr() for k in ("X", "Y", "ell"))
+                g.pol_L = self.rbf.fact_ws.data_ptr()
+            self.gbuf["m0"] = torch.empty((R, Ds), dtype=F64, device=d)
+            self.gbuf["S0"] = torch.empty((R, Ds, Ds), dtype=F64, device=d)
+            g.gm0, g.gS0 = self.gbuf["m0"].data_ptr(), self.gbuf["S0"].data_ptr()
+            wsb = lib.pilco_rollout_bwd_workspace_bytes(C.byref(self.ro))
+            self.bws = torch.empty(max(wsb // 8, 2), dtype=F64, device=d)
+            g.ws, g.ws_bytes = self.bws.data_ptr(), wsb
+            self.grad = g
+        check(lib.pilco_rollout_backward(C.byref(self.ro), C.byref(self.grad), stream_ptr()), "rollout_backward")
+        return self.gbuf

@@ -1,0 +1,213 @@
+"""Policy optimisation with batched random restarts (replaces the sequential restart loop of
+``PILCO.optimize_policy``, pilco/models/pilco.py:75-113).
+
+* All restarts of this rank are evaluated in ONE batched device rollout (forward + reverse sweep).
+* Each restart is driven by its own SciPy L-BFGS-B instance (the optimiser the reference uses through
+  ``gpflow.optimizers.Scipy``); the instances run in worker threads that advance in lock step, so every
+  device call evaluates the current trial points of all still-active restarts.
+* Multi-GPU: restart r belongs to rank r % world; after the local optimisations a single
+  ``all_gather`` of ``[loss | flat parameters]`` lets every rank pick the same winner (ties -> lowest
+  restart index, the sequential ``>`` comparison of pilco.py:105).  No other collective is used.
+"""
+import threading
+
+import numpy as np
+import scipy.optimize
+import torch
+
+from . import engine, controllers, _lib
+
+BIG = 1e10
+
+
+class PolicyEvaluator:
+    """loss(flat) = -sum_t E[r(x_t)] and its gradient for a batch of flat policy parameter vectors."""
+
+    def __init__(self, pilco, R):
+        self.pilco, self.R = pilco, R
+        c = pilco.controller
+        self.c = c
+        self.linear = isinstance(c, controllers.LinearController)
+        flat0 = np.tile(c.get_flat(), (R, 1))
+        self.P = flat0.shape[1]
+        if self.linear:
+            U, Ds = c.W.shape
+            spec = c.policy_spec(flat0)
+        else:
+            bf, Ds, U = c.policy_shapes
+            spec = pilco.policy_spec(flat0)
+            self.gp = spec["gp"]
+        self.shape = (Ds, U)
+        self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, pilco.reward.terms(),
+                                       np.asarray(pilco.m_init, dtype=np.float64).reshape(-1),
+                                       np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=R)
+        self.h_flat = torch.empty((R, self.P), dtype=torch.float64).pin_memory()
+        self.h_out = torch.empty((R, self.P + 2), dtype=torch.float64).pin_memory()
+        self.d_flat = torch.empty((R, self.P), dtype=torch.float64, device=engine.device())
+        self.d_out = torch.empty((R, self.P + 2), dtype=torch.float64, device=engine.device())
+
+    def __call__(self, flats):
+        """flats [R,P] (numpy) -> loss [R], grad [R,P]; non-finite restarts get (BIG, 0)."""
+        R, P = self.R, self.P
+        Ds, U = self.shape
+        self.h_flat.copy_(torch.as_tensor(flats))
+        self.d_flat.copy_(self.h_flat, non_blocking=True)
+        plan = self.plan
+        if self.linear:
+            plan.W.copy_(self.d_flat[:, :U * Ds].reshape(R, U, Ds))
+            plan.b.copy_(self.d_flat[:, U * Ds:].reshape(R, U))
+        else:
+            gp = self.gp
+            bf = gp.n
+            th = self.d_flat[:, bf * Ds + bf * U:].reshape(R, U, Ds)
+            gp.X.copy_(self.d_flat[:, :bf * Ds].reshape(R, bf, Ds))
+            gp.Y.copy_(self.d_flat[:, bf * Ds:bf * Ds + bf * U].reshape(R, bf, U))
+            gp.ell.copy_(1e-3 + torch.nn.functional.softplus(th))
+            engine.gp_refactorize(gp)
+        plan.forward()
+        g = plan.backward()
+        out = self.d_out
+        out[:, 0] = -plan.reward
+        out[:, 1] = torch.maximum(plan.info, gp.info if not self.linear else plan.info).to(torch.float64)
+        if self.linear:
+            out[:, 2:2 + U * Ds] = -g["W"].reshape(R, -1)
+            out[:, 2 + U * Ds:] = -g["b"].reshape(R, -1)
+        else:
+            bf = self.gp.n
+            out[:, 2:2 + bf * Ds] = -g["X"].reshape(R, -1)
+            out[:, 2 + bf * Ds:2 + bf * Ds + bf * U] = -g["Y"].reshape(R, -1)
+            out[:, 2 + bf * Ds + bf * U:] = -(g["ell"] * torch.sigmoid(th)).reshape(R, -1)
+        self.h_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        res = self.h_out.numpy()
+        loss, bad, grad = res[:, 0].copy(), res[:, 1] != 0, res[:, 2:].copy()
+        bad |= ~np.isfinite(loss) | ~np.isfinite(grad).all(axis=1)
+        loss[bad] = BIG
+        grad[bad] = 0.0
+        return loss, grad
+
+
+class LockstepLBFGS:
+    """R independent SciPy L-BFGS-B runs whose objective evaluations are served in batches."""
+
+    def __init__(self, evaluate, x0, maxiter):
+        self.evaluate, self.x = evaluate, np.array(x0, dtype=np.float64)
+        self.R = self.x.shape[0]
+        self.maxiter = maxiter
+        self.cv = threading.Condition()
+        self.pending = [False] * self.R
+        self.active = [True] * self.R
+        self.result = [None] * self.R
+        self.generation = 0
+        self.final = [None] * self.R
+        self.errors = []
+
+    def _worker(self, i):
+        def fun(x):
+            with self.cv:
+                self.x[i] = x
+                self.pending[i] = True
+                gen = self.generation
+                self.cv.notify_all()
+                while self.generation == gen:
+                    self.cv.wait()
+                f, g = self.result[i]
+            return f, g
+        try:
+            res = scipy.optimize.minimize(fun, self.x[i].copy(), jac=True, method="L-BFGS-B",
+                                          options=dict(maxiter=self.maxiter))
+            self.final[i] = (float(res.fun), np.array(res.x))
+        except Exception as exc:          # pragma: no cover
+            self.errors.append(exc)
+        finally:
+            with self.cv:
+                self.active[i] = False
+                self.cv.notify_all()
+
+    def run(self):
+        threads = [threading.Thread(target=self._worker, args=(i,), daemon=True) for i in range(self.R)]
+        for t in threads:
+            t.start()
+        while True:
+            with self.cv:
+                while any(self.active[i] and not self.pending[i] for i in range(self.R)):
+                    self.cv.wait()
+                if not any(self.active):
+                    break
+                xs = self.x.copy()
+            loss, grad = self.evaluate(xs)                 # device work happens on this (main) thread
+            with self.cv:
+                for i in range(self.R):
+                    if self.pending[i]:
+                        self.result[i] = (float(loss[i]), grad[i].copy())
+                        self.pending[i] = False
+                self.generation += 1
+                self.cv.notify_all()
+        for t in threads:
+            t.join()
+        if self.errors:
+            raise self.errors[0]
+        return self.final
+
+
+def shard_restarts(restarts, rank, world):
+    """restart r -> rank r % world."""
+    return [r for r in range(restarts) if r % world == rank]
+
+
+def select_best(table):
+    """table [restarts, 1+P] = [loss | flat]; lowest loss wins, ties -> lowest restart index."""
+    losses = table[:, 0]
+    best = int(np.flatnonzero(losses == np.nanmin(losses))[0]) if np.isfinite(losses).any() else 0
+    return best
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def initial_flats(controller, restarts):
+    """Restart 0 starts from the current parameters, restarts 1.. from ``controller.randomize()``
+    (pilco.py:94-99).  Every rank draws the same sequence from the global numpy RNG."""
+    flats = [controller.get_flat()]
+    saved = flats[0].copy()
+    for _ in range(restarts - 1):
+        controller.randomize()
+        flats.append(controller.get_flat())
+    controller.set_flat(saved)
+    return np.stack(flats)
+
+
+def optimize(pilco, maxiter=50, restarts=1):
+    """Returns (best_flat, best_reward, per-restart rewards)."""
+    restarts = max(int(restarts), 1)
+    dist, rank, world = _dist()
+    flats0 = initial_flats(pilco.controller, restarts)
+    mine = shard_restarts(restarts, rank, world)
+    P = flats0.shape[1]
+    local = np.full((restarts, 1 + P), np.nan)
+    if mine:
+        ev = PolicyEvaluator(pilco, len(mine))
+        finals = LockstepLBFGS(ev, flats0[mine], maxiter).run()
+        xs = np.stack([f[1] for f in finals])
+        loss, _ = ev(xs)                                   # rewards at the final points (pilco.py:96,103)
+        for k, r in enumerate(mine):
+            local[r, 0] = loss[k]
+            local[r, 1:] = xs[k]
+    if world > 1:
+        dev = engine.device()
+        per = (restarts + world - 1) // world
+        send = torch.full((per, 1 + P), float("nan"), dtype=torch.float64, device=dev)
+        if mine:
+            send[:len(mine)] = torch.as_tensor(local[mine], device=dev)
+        gathered = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(gathered, send)                    # the one collective of the hot path
+        for g_rank, t in enumerate(gathered):
+            rows = shard_restarts(restarts, g_rank, world)
+            if rows:
+                local[rows] = t[:len(rows)].cpu().numpy()
+    best = select_best(local)
+    return local[best, 1:], -float(local[best, 0]), [-float(v) for v in local[:, 0]]
