@@ -22,8 +22,12 @@ mrun          a small MATLAB-subset interpreter that executes the reference's ``
               transcriptions and to generate ``tests/golden/*.npz``.
 
 Pinning status: the reference commits NO golden vectors (its tests call Octave live) and
-TensorFlow/GPflow/Octave are not installable here.  The oracle is pinned by (1) executing
-the reference's own ``.m`` files with ``oracle/mrun.py`` and (2) the cross-agreement of the
-two independent transcriptions (the exact relation the reference's tests assert, at
-rtol 1e-4; ours agree to <=1e-9).  See DESIGN.md "Oracle".
+TensorFlow/GPflow/Octave are not installable here.  The oracle is pinned by (1) executing the
+reference's own ``.m`` oracle files with ``oracle/mrun.py`` (transcriptions match to <=2e-12;
+outputs committed as ``tests/golden/*.npz`` with ``tests/golden/make_golden.py``) and (2) the
+cross-agreement of the two independent transcriptions -- the exact relation the reference's tests
+assert at rtol 1e-4; ours agree to <=1e-9.  The reference's Python/TensorFlow side itself was never
+executed here (not installable).  Gradients and optimiser trajectories: parity unpinned by the
+reference (no reference test checks them); gradients are checked against torch autograd.
+See DESIGN.md section 8.
 """

@@ -169,6 +169,28 @@ def _dist():
     return None, 0, 1
 
 
+def gather_table(local, restarts, rank, world, dist):
+    """One all_gather of the per-restart rows ``[loss | flat]`` (NCCL over NVLink on the GPU box, gloo in the
+    CPU tests).  Rows of restarts owned by other ranks are NaN on input and filled on output."""
+    if world <= 1:
+        return local
+    P1 = local.shape[1]
+    dev = engine.device() if dist.get_backend() == "nccl" else torch.device("cpu")
+    per = (restarts + world - 1) // world
+    mine = shard_restarts(restarts, rank, world)
+    send = torch.full((per, P1), float("nan"), dtype=torch.float64, device=dev)
+    if mine:
+        send[:len(mine)] = torch.as_tensor(local[mine]).to(dev)
+    gathered = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(gathered, send)                        # the one collective of the hot path
+    out = local.copy()
+    for g_rank, t in enumerate(gathered):
+        rows = shard_restarts(restarts, g_rank, world)
+        if rows:
+            out[rows] = t[:len(rows)].cpu().numpy()
+    return out
+
+
 def initial_flats(controller, restarts):
     """Restart 0 starts from the current parameters, restarts 1.. from ``controller.randomize()``
     (pilco.py:94-99).  Every rank draws the same sequence from the global numpy RNG."""
@@ -197,17 +219,6 @@ def optimize(pilco, maxiter=50, restarts=1):
         for k, r in enumerate(mine):
             local[r, 0] = loss[k]
             local[r, 1:] = xs[k]
-    if world > 1:
-        dev = engine.device()
-        per = (restarts + world - 1) // world
-        send = torch.full((per, 1 + P), float("nan"), dtype=torch.float64, device=dev)
-        if mine:
-            send[:len(mine)] = torch.as_tensor(local[mine], device=dev)
-        gathered = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(gathered, send)                    # the one collective of the hot path
-        for g_rank, t in enumerate(gathered):
-            rows = shard_restarts(restarts, g_rank, world)
-            if rows:
-                local[rows] = t[:len(rows)].cpu().numpy()
+    local = gather_table(local, restarts, rank, world, dist)
     best = select_best(local)
     return local[best, 1:], -float(local[best, 0]), [-float(v) for v in local[:, 0]]

@@ -1,0 +1,147 @@
+"""CPU tests of the host-side logic: C-ABI symbols, parameter objects, GP training driver, the lock-step
+optimiser, restart sharding / winner selection, the oct2py/gpflow stand-ins, and the loud failure of the
+product path without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pilco_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pilco_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(os.path.join(ROOT, "pilco_b200", "libpilco_b200.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libpilco_b200.so does not export %s" % name
+    from pilco_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.lib.pilco_version() == 1
+    assert _lib.lib.pilco_pad_n(300) == 320 and _lib.lib.pilco_pad_n(64) == 64
+    assert _lib.lib.pilco_mm_workspace_bytes(300, 12, 10, 2) > 0
+    assert _lib.lib.pilco_mm_workspace_bytes(300, 17, 10, 2) == 0          # D > PILCO_MAX_D rejected
+    assert b"workspace" in _lib.lib.pilco_status_string(-3)
+
+
+def test_struct_layouts_match_header_sizes():
+    from pilco_b200 import _lib
+    assert ctypes.sizeof(_lib.GpModel) == 4 * 4 + 4 * 16 + 16          # ints, 4x(ptr,stride), iK+ldk(+pad)
+    assert ctypes.sizeof(_lib.RewardTerm) == 32
+    assert ctypes.sizeof(_lib.Rollout) % 8 == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    from pilco.models import MGPR
+    X = np.random.rand(20, 2); Y = np.random.rand(20, 1)
+    m = MGPR((X, Y))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        m.predict_on_noisy_inputs(np.zeros((1, 2)), np.eye(2))
+
+
+def test_parameter_surface():
+    from pilco_b200.params import Parameter, Softplus, set_trainable
+    p = Parameter(np.ones(3), transform=Softplus(1e-3))
+    assert p.shape == (3,) and np.allclose(p.numpy(), 1.0)
+    th = p.unconstrained
+    assert np.allclose(1e-3 + np.logaddexp(0, th), 1.0)
+    p.assign([1.0, 2.0, 3.0])
+    assert np.allclose(np.stack([p, p]), [[1, 2, 3], [1, 2, 3]])
+    assert np.allclose(p.value() * 2, [2, 4, 6]) and np.allclose(2 * p, [2, 4, 6])
+    set_trainable(p, False)
+    assert not p.trainable
+    q = Parameter(0.5)
+    assert isinstance(q.numpy(), float) and q.shape == ()
+
+
+def test_gp_training_reduces_loss_and_restarts_keep_best():
+    from pilco.models import MGPR
+    np.random.seed(0)
+    X = np.random.rand(40, 2)
+    Y = np.sin(3 * X).dot(np.random.rand(2, 1)) + 1e-2 * np.random.randn(40, 1)
+    m = MGPR((X, Y))
+    l0 = m.models[0].training_loss()
+    m.optimize(restarts=1)
+    l1 = m.models[0].training_loss()
+    assert l1 < l0 and np.all(m.lengthscales > 0) and np.all(m.noise >= 1e-6)
+    m.models[0].likelihood.variance.assign(0.01)
+    from gpflow import set_trainable
+    set_trainable(m.models[0].likelihood.variance, False)
+    m.optimize(restarts=0)
+    assert abs(m.noise[0] - 0.01) < 1e-12
+
+
+def test_smgpr_and_controller_host_surface():
+    from pilco.models import SMGPR
+    from pilco.controllers import RbfController, LinearController
+    np.random.seed(0)
+    X = np.random.rand(30, 3); Y = np.random.rand(30, 2)
+    s = SMGPR((X, Y), num_induced_points=7)
+    assert s.Z.numpy().shape == (7, 3) and s.centres.shape == (7, 3)
+    rbf = RbfController(3, 2, 11, max_action=2.0)
+    assert rbf.models[1].X is rbf.models[0].X                          # shared centres (controllers.py:103-106)
+    assert not rbf.models[0].kernel.variance.trainable and not rbf.models[0].likelihood.variance.trainable
+    flat = rbf.get_flat()
+    assert flat.shape == (11 * 3 + 11 * 2 + 2 * 3,)
+    rbf.randomize()
+    rbf.set_flat(flat)
+    assert np.allclose(rbf.get_flat(), flat)
+    rbf.set_data((np.random.rand(11, 3), np.random.rand(11, 2)))
+    assert rbf.X.shape == (11, 3) and rbf.Y.shape == (11, 2)
+    lin = LinearController(3, 2)
+    f = lin.get_flat(); lin.randomize(); lin.set_flat(f)
+    assert np.allclose(lin.get_flat(), f)
+
+
+def test_lockstep_lbfgs_batches_evaluations():
+    from pilco_b200.policy_opt import LockstepLBFGS
+    A = np.array([1.0, 3.0, 10.0, 0.5])
+    c = np.array([[1, 2], [3, -1], [0.5, 0.5], [-2, 4]], dtype=float)
+    batches = []
+
+    def ev(x):
+        batches.append(x.copy())
+        return (A[:, None] * (x - c) ** 2).sum(1), 2 * A[:, None] * (x - c)
+    fin = LockstepLBFGS(ev, np.zeros((4, 2)), 50).run()
+    for (f, x), ci in zip(fin, c):
+        assert f < 1e-12 and np.allclose(x, ci, atol=1e-6)
+    assert len(batches) < 12            # evaluations are shared: ~max over restarts, not the sum
+
+
+def test_lockstep_isolates_nonfinite_restart():
+    from pilco_b200.policy_opt import LockstepLBFGS, BIG
+
+    def ev(x):
+        f = (x ** 2).sum(1); g = 2 * x
+        f[1] = BIG; g[1] = 0.0          # restart 1 always fails (what the evaluator reports for info != 0)
+        return f, g
+    fin = LockstepLBFGS(ev, np.ones((3, 2)), 20).run()
+    assert fin[0][0] < 1e-12 and fin[2][0] < 1e-12 and fin[1][0] == BIG
+
+
+def test_shard_and_select():
+    from pilco_b200.policy_opt import shard_restarts, select_best
+    assert shard_restarts(10, 0, 4) == [0, 4, 8] and shard_restarts(10, 3, 4) == [3, 7]
+    assert sorted(sum((shard_restarts(7, r, 3) for r in range(3)), [])) == list(range(7))
+    t = np.array([[2.0, 0], [1.0, 0], [1.0, 1], [np.nan, 0]])
+    assert select_best(t) == 1          # ties -> lowest restart index (pilco.py:105 uses a strict >)
+
+
+def test_oct2py_stand_in_conventions():
+    import oct2py
+    oc = oct2py.Oct2Py()
+    oc.addpath("whatever")
+    s = oct2py.io.Struct(); s.hyp = 1; s.p = oct2py.io.Struct(); s.p.w = 2
+    assert s["hyp"] == 1 and s.p.w == 2
+    M, S, C = oc.gSin(np.array([[0.1], [0.2]]), 0.1 * np.eye(2), 7.0, nout=3)
+    assert M.shape == (2, 1) and S.shape == (2, 2) and C.shape == (2, 2)
+    out = oc.reward(np.zeros((2, 1)), np.eye(2), np.zeros((2, 1)), np.eye(2), nout=4)
+    assert len(out) == 4 and isinstance(out[0], float)
+    from gpflow import config
+    assert config.default_float() is np.float64
