@@ -12,6 +12,11 @@
 // -------------------------------------------------------------------------------------------------
 // backward tile kernel
 // -------------------------------------------------------------------------------------------------
+static inline __host__ __device__ size_t mm_btile_smem_bytes(int np, int ldz) {
+    const int cm = np < TILE_CM ? np : TILE_CM;
+    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
+}
+
 template <int KS>
 __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
     constexpr int DP = 4 * KS;
@@ -441,11 +446,12 @@ __global__ void __launch_bounds__(128) mm_breduce_kernel(MMBwdParams bp) {
 // -------------------------------------------------------------------------------------------------
 template <int KS>
 static int launch_btile(const MMBwdParams& bp, cudaStream_t st) {
-    const size_t smem = mm_tile_smem_bytes(bp.B.F.np, bp.B.F.ldz);
+    const size_t smem = mm_btile_smem_bytes(bp.B.F.np, bp.B.F.ldz);
+    { int rc0 = exp_table_upload(); if (rc0) return rc0; }
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(mm_btile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)mm_tile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
+                                 (int)mm_btile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }
     dim3 grid(bp.B.F.NB, bp.B.P2, bp.f.R);
@@ -460,12 +466,12 @@ int mm_backward_launch(MMBwdParams bp, cudaStream_t st) {
     sp.L = bp.B.F; sp.bwd = 1; sp.oQ = bp.B.oQ; sp.oC = bp.B.oC; sp.oLd = bp.B.oLd;
     // per-restart stride of the setup arrays must be the backward stride
     sp.L.per_r = bp.B.per_r;
-    dim3 gs(E * E, R);
+    dim3 gs((E * E + SETUP_WARPS - 1) / SETUP_WARPS, R);
     switch (ks) {
-        case 1: mm_setup_kernel<4, true><<<gs, 128, 0, st>>>(sp); break;
-        case 2: mm_setup_kernel<8, true><<<gs, 128, 0, st>>>(sp); break;
-        case 3: mm_setup_kernel<12, true><<<gs, 128, 0, st>>>(sp); break;
-        default: mm_setup_kernel<16, true><<<gs, 128, 0, st>>>(sp); break;
+        case 1: mm_setup_kernel<4, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
+        case 2: mm_setup_kernel<8, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
+        case 3: mm_setup_kernel<12, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
+        default: mm_setup_kernel<16, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
     }
     CUDA_LAUNCH_CHECK();
     int rc;

@@ -12,6 +12,15 @@ int mm_check_model(const pilco_gp_model* gp) {
     return PILCO_OK;
 }
 
+// pair slices per (row block, restart): enough CTAs for >= ~3 resident waves of 2 CTAs/SM, at most P
+static int tile_slices(const MMParams& p) {
+    const long long base = (long long)p.L.NB * p.R;
+    long long S = (148LL * 2 * 3 + base - 1) / base;
+    if (S > p.L.P) S = p.L.P;
+    if (S < 1) S = 1;
+    return (int)S;
+}
+
 template <int KS>
 static int launch_tile(const MMParams& p, cudaStream_t st) {
     const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
@@ -21,20 +30,23 @@ static int launch_tile(const MMParams& p, cudaStream_t st) {
                                  (int)mm_tile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }
-    dim3 grid(p.L.NB, p.L.P, p.R);
-    mm_tile_kernel<KS><<<grid, 256, smem, st>>>(p);
+    int rc = exp_table_upload();
+    if (rc) return rc;
+    const int S = tile_slices(p);
+    dim3 grid(p.L.NB, S, p.R);
+    mm_tile_kernel<KS><<<grid, 256, smem, st>>>(p, S);
     return PILCO_OK;
 }
 
 int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
     const int E = p.gp.E, D = p.gp.D;
-    dim3 gs(E + p.L.P, p.R);
+    dim3 gs((E + p.L.P + SETUP_WARPS - 1) / SETUP_WARPS, p.R);
     const int ks = ksteps_of(D);
     switch (ks) {
-        case 1: mm_setup_kernel<4, false><<<gs, 128, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8, false><<<gs, 128, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12, false><<<gs, 128, 0, st>>>(p); break;
-        default: mm_setup_kernel<16, false><<<gs, 128, 0, st>>>(p); break;
+        case 1: mm_setup_kernel<4, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        default: mm_setup_kernel<16, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
     }
     CUDA_LAUNCH_CHECK();
     int rc;
@@ -95,13 +107,13 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
     cudaEvent_t ev[4];
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
     const int E = gp->E, ks = ksteps_of(gp->D);
-    dim3 gs(E + p.L.P, R);
+    dim3 gs((E + p.L.P + SETUP_WARPS - 1) / SETUP_WARPS, R);
     cudaEventRecord(ev[0], st);
     switch (ks) {
-        case 1: mm_setup_kernel<4, false><<<gs, 128, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8, false><<<gs, 128, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12, false><<<gs, 128, 0, st>>>(p); break;
-        default: mm_setup_kernel<16, false><<<gs, 128, 0, st>>>(p); break;
+        case 1: mm_setup_kernel<4, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 2: mm_setup_kernel<8, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 3: mm_setup_kernel<12, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        default: mm_setup_kernel<16, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
     }
     cudaEventRecord(ev[1], st);
     switch (ks) {

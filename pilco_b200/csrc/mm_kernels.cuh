@@ -12,6 +12,8 @@
 #pragma once
 #include "common.cuh"
 
+#define TILE_CM 512        // columns staged in shared memory per chunk
+
 struct MMWs {            // workspace layout, offsets in doubles relative to the per-restart base
     size_t zeta, betap, Ap, Bq, U, Tpart, per_r;
     int np, ldz, P, NB;
@@ -26,7 +28,7 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     L.Ap = o;    o += (size_t)L.P * L.np;
     L.Bq = o;    o += (size_t)L.P * L.np;
     L.U = o;     o += (size_t)L.P * L.np * L.ldz;
-    L.Tpart = o; o += (size_t)L.P * L.NB;
+    L.Tpart = o; o += (size_t)L.P * (L.np / 64) * 8 * ((L.np + TILE_CM - 1) / TILE_CM);
     L.per_r = (o + 1) & ~(size_t)1;
     return L;
 }
@@ -46,40 +48,73 @@ struct MMParams {
     size_t oQ, oC, oLd;
 };
 
-#define TILE_CM 512        // columns staged in shared memory per chunk
 
 #ifdef __CUDACC__
 
 // -------------------------------------------------------------------------------------------------
-// setup
+// setup: ONE WARP PER TASK (4 tasks per CTA).  The D x D Cholesky runs in registers (lane i owns row i,
+// column broadcasts by shuffle), the triangular solves keep each right-hand side in registers and read
+// L from per-warp shared memory, the per-centre loop strides the 32 lanes over the centres.
 // -------------------------------------------------------------------------------------------------
+#define SETUP_WARPS 4
+
+// lane i (< DP) holds row i of the SPD matrix in a[0..DP); on exit row i of its lower Cholesky factor.
+// Returns false if a pivot is not positive (all lanes agree).
 template <int DP>
-__device__ __forceinline__ void load_sym_s(const double* __restrict__ s, int D, double* s_s) {
-    // s_s[i][j] = 0.5 (s[i][j] + s[j][i]), zero padded to DP
-    for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
-        const int i = e / DP, j = e % DP;
-        s_s[i * SLD + j] = (i < D && j < D) ? 0.5 * (s[i * D + j] + s[j * D + i]) : 0.0;
+__device__ __forceinline__ bool chol_regs(double (&a)[DP], int lane) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < DP; ++j) {
+        double d = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        const double piv = sqrt(d);
+        const double lij = (lane == j) ? piv : a[j] / piv;
+        a[j] = lij;
+#pragma unroll
+        for (int k = j + 1; k < DP; ++k) {
+            const double lkj = __shfl_sync(0xffffffffu, lij, k);
+            if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+        }
+    }
+    return ok;
+}
+
+// Solve (L L^T) x = y for the right-hand side held in y[0..DP) (one per lane); L in shared memory [DP][SLD].
+template <int DP>
+__device__ __forceinline__ void chol_solve_regs(const double* __restrict__ Ls, double (&y)[DP]) {
+#pragma unroll
+    for (int i = 0; i < DP; ++i) {
+        double v = y[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v = fma(-Ls[i * SLD + k], y[k], v);
+        y[i] = v / Ls[i * SLD + i];
+    }
+#pragma unroll
+    for (int i = DP - 1; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < DP; ++k) v = fma(-Ls[k * SLD + i], y[k], v);
+        y[i] = v / Ls[i * SLD + i];
     }
 }
 
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
-    const int r = blockIdx.y, task = BWD ? blockIdx.x + p.gp.E : blockIdx.x;   // BWD: pair tasks only
+__global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) {
+    const int r = blockIdx.y;
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
     const MMWs& L = p.L;
     const int np = L.np, ldz = L.ldz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntask = BWD ? L.P : E + L.P;
+    const int task0 = blockIdx.x * SETUP_WARPS + warp;
+    const int task = BWD ? task0 + E : task0;                  // BWD: pair tasks only (ordered pairs)
 
-    __shared__ double s_s[MAXD * SLD];      // symmetrised input covariance
-    __shared__ double sA[MAXD * SLD];       // matrix being factored
-    __shared__ double sB[MAXD * SLD];       // W_a or Q_ab
-    __shared__ double sC[BWD ? MAXD * SLD : 1];   // BWD: (s + diag(1/delta))^-1
-    __shared__ double sinvd[MAXD];
-    __shared__ double sm[MAXD], spa[MAXD], spb[MAXD], sdinv[MAXD];
-    __shared__ double sred[(MAXD + 1) * 4], sout[MAXD + 1];
-    __shared__ double slogdet;
-    __shared__ int sok;
+    __shared__ double s_s[MAXD * SLD];                         // symmetrised input covariance (all warps)
+    __shared__ double sm[MAXD];
+    __shared__ double sLw[SETUP_WARPS][MAXD * SLD];            // per warp: Cholesky factor
+    __shared__ double sQw[SETUP_WARPS][MAXD * SLD];            // per warp: W_a or Q_ab
+    __shared__ double spw[SETUP_WARPS][3][MAXD];               // per warp: p_a / ell^2, p_b, 1/(p_a+p_b)
 
     const double* X = gp.X + (size_t)r * gp.X_bs;
     const double* ell = gp.ell + (size_t)r * gp.ell_bs;
@@ -89,39 +124,57 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
     const double* sr = p.s + (size_t)r * p.s_rs;
     double* wsr = p.ws + (size_t)r * L.per_r;
 
-    load_sym_s<DP>(sr, D, s_s);
+    for (int e = tid; e < DP * DP; e += blockDim.x) {
+        const int i = e / DP, j = e % DP;
+        s_s[i * SLD + j] = (i < D && j < D) ? 0.5 * (sr[i * D + j] + sr[j * D + i]) : 0.0;
+    }
     if (tid < DP) sm[tid] = tid < D ? mr[tid] : 0.0;
     __syncthreads();
+    if (task0 >= ntask) return;
+
+    double* Ls = sLw[warp];
+    double* Qs = sQw[warp];
+    double* pa = spw[warp][0];
+    double* pb = spw[warp][1];
+    double* dinv = spw[warp][2];
+    const int li = lane < DP ? lane : DP - 1;                  // clamp so idle lanes read valid memory
 
     if (!BWD && task < E) {
         // ---------------- output task: mean and input-output covariance of GP a ----------------
         const int a = task;
-        if (tid < DP) { const double l = tid < D ? ell[a * D + tid] : 1.0; spa[tid] = l * l; }
-        __syncthreads();
-        for (int e = tid; e < DP * DP; e += blockDim.x) {
-            const int i = e / DP, j = e % DP;
-            sA[i * SLD + j] = s_s[i * SLD + j] + (i == j ? spa[i] : 0.0);
-            sB[i * SLD + j] = (i == j) ? 1.0 : 0.0;
+        if (lane < DP) { const double l = lane < D ? ell[a * D + lane] : 1.0; pa[lane] = l * l; }
+        __syncwarp();
+        double arow[DP];
+#pragma unroll
+        for (int j = 0; j < DP; ++j) arow[j] = s_s[li * SLD + j] + (j == li ? pa[li] : 0.0);
+        const bool ok = chol_regs<DP>(arow, lane);
+        if (lane < DP) {
+#pragma unroll
+            for (int j = 0; j < DP; ++j) Ls[lane * SLD + j] = arow[j];
         }
-        __syncthreads();
-        if (warp == 0) {
-            const bool ok = chol_warp(sA, sinvd, DP, lane);
-            chol_solve_warp(sA, sinvd, sB, DP, DP, lane);        // sB = (s + Lambda^2)^-1
-            if (lane == 0) {
-                double ld = chol_logdet(sinvd, DP), sl = 0.0;
-                for (int d = 0; d < D; ++d) sl += log(spa[d]);
-                slogdet = log(sf2[a]) + 0.5 * (sl - ld);         // log c_a   (padded dims: log 1 = 0)
-                sok = ok ? 1 : 0;
-            }
+        __syncwarp();
+        double y[DP];
+#pragma unroll
+        for (int i = 0; i < DP; ++i) y[i] = (i == li) ? 1.0 : 0.0;
+        chol_solve_regs<DP>(Ls, y);                            // column `lane` of W = (s + Lambda^2)^-1
+        if (lane < DP) {
+#pragma unroll
+            for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = y[i];
         }
-        __syncthreads();
-        if (tid == 0 && !sok && p.info) atomicOr(&p.info[r], 1);
+        double ld = 0.0, sl = 0.0;
+#pragma unroll
+        for (int j = 0; j < DP; ++j) ld += log(Ls[j * SLD + j]);
+        for (int d = 0; d < D; ++d) sl += log(pa[d]);
+        const double c = exp(log(sf2[a]) + 0.5 * sl - ld);     // sf2 sqrt(prod ell^2 / det(s + Lambda^2))
+        if (lane == 0 && !ok && p.info) atomicOr(&p.info[r], 1);
+        __syncwarp();
 
         double acc[DP + 1];
 #pragma unroll
         for (int i = 0; i <= DP; ++i) acc[i] = 0.0;
-        for (int nn = tid; nn < np; nn += blockDim.x) {
+        for (int nn = lane; nn < np; nn += 32) {
             double z[DP];
+            double bw = 0.0;
             if (nn < n) {
 #pragma unroll
                 for (int d = 0; d < DP; ++d) z[d] = d < D ? X[(size_t)nn * D + d] - sm[d] : 0.0;
@@ -130,85 +183,96 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
                 for (int i = 0; i < DP; ++i) {
                     double v = 0.0;
 #pragma unroll
-                    for (int j = 0; j < DP; ++j) v = fma(sB[i * SLD + j], z[j], v);
+                    for (int j = 0; j < DP; ++j) v = fma(Qs[i * SLD + j], z[j], v);
                     t[i] = v; e = fma(z[i], v, e);
                 }
-                const double bw = beta[(size_t)a * n + nn];
+                bw = beta[(size_t)a * n + nn];
                 const double w = bw * exp(-0.5 * e);
                 acc[DP] += w;
 #pragma unroll
                 for (int i = 0; i < DP; ++i) acc[i] = fma(w, t[i], acc[i]);
-                wsr[L.betap + (size_t)a * np + nn] = bw;
             } else {
 #pragma unroll
                 for (int d = 0; d < DP; ++d) z[d] = 0.0;
-                wsr[L.betap + (size_t)a * np + nn] = 0.0;
             }
+            wsr[L.betap + (size_t)a * np + nn] = bw;
             if (a == 0) {
-                for (int d = 0; d < ldz; ++d) wsr[L.zeta + (size_t)nn * ldz + d] = d < DP ? z[d] : 0.0;
+                double* zp = wsr + L.zeta + (size_t)nn * ldz;
+#pragma unroll
+                for (int d = 0; d < DP; ++d) zp[d] = z[d];
+                for (int d = DP; d < ldz; ++d) zp[d] = 0.0;
             }
         }
-        block_sum<DP + 1>(acc, DP + 1, sred, sout);
-        const double c = exp(slogdet);
-        if (tid == 0) p.M[(size_t)r * E + a] = c * sout[DP];
-        if (tid < D) p.V[((size_t)r * D + tid) * E + a] = c * sout[tid];
+#pragma unroll
+        for (int i = 0; i <= DP; ++i) acc[i] = warp_sum(acc[i]);
+        if (lane == 0) p.M[(size_t)r * E + a] = c * acc[DP];
+#pragma unroll
+        for (int i = 0; i < DP; ++i)
+            if (lane == i && i < D) p.V[((size_t)r * D + i) * E + a] = c * acc[i];
         return;
     }
 
-    // ---------------- pair task (a <= b): Q_ab and the per-centre exponent pieces ----------------
+    // ---------------- pair task: Q_ab and the per-centre exponent pieces ----------------
     const int q = task - E;
     int a, b;
     if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);
-    if (tid < DP) {
-        const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
-        spa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
-        spb[tid] = tid < D ? 1.0 / (lb * lb) : 0.0;
-        sdinv[tid] = tid < D ? 1.0 / (1.0 / (la * la) + 1.0 / (lb * lb)) : 0.0;    // 1/(p_a+p_b)
+    if (lane < DP) {
+        const double la = lane < D ? ell[a * D + lane] : 1.0, lb = lane < D ? ell[b * D + lane] : 1.0;
+        pa[lane] = lane < D ? 1.0 / (la * la) : 0.0;
+        pb[lane] = lane < D ? 1.0 / (lb * lb) : 0.0;
+        dinv[lane] = lane < D ? 1.0 / (1.0 / (la * la) + 1.0 / (lb * lb)) : 0.0;      // 1/(p_a+p_b)
     }
-    __syncthreads();
-    // A = s + diag(1/(p_a+p_b));  padded dims get 1 on the diagonal (s is zero there)
-    for (int e = tid; e < DP * DP; e += blockDim.x) {
-        const int i = e / DP, j = e % DP;
-        const double dd = (i < D) ? sdinv[i] : 1.0;
-        sA[i * SLD + j] = s_s[i * SLD + j] + (i == j ? dd : 0.0);
-        sB[i * SLD + j] = s_s[i * SLD + j];
-        if (BWD) sC[i * SLD + j] = (i == j) ? 1.0 : 0.0;
+    __syncwarp();
+    double arow[DP];
+#pragma unroll
+    for (int j = 0; j < DP; ++j) arow[j] = s_s[li * SLD + j] + (j == li ? (li < D ? dinv[li] : 1.0) : 0.0);
+    const bool ok = chol_regs<DP>(arow, lane);
+    if (lane < DP) {
+#pragma unroll
+        for (int j = 0; j < DP; ++j) Ls[lane * SLD + j] = arow[j];
     }
-    __syncthreads();
-    if (warp == 0) {
-        const bool ok = chol_warp(sA, sinvd, DP, lane);
-        chol_solve_warp(sA, sinvd, sB, DP, DP, lane);            // sB = (s + Dd^-1)^-1 s
-        if (BWD) chol_solve_warp(sA, sinvd, sC, DP, DP, lane);   // sC = (s + Dd^-1)^-1
-        if (lane == 0) {
-            double ld = chol_logdet(sinvd, DP);
-            for (int d = 0; d < D; ++d) ld += log(spa[d] + spb[d]);
-            slogdet = ld;                                        // log det R_ab
-            sok = ok ? 1 : 0;
-        }
+    __syncwarp();
+    double y[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) y[i] = s_s[i * SLD + li];     // column `lane` of s
+    chol_solve_regs<DP>(Ls, y);                                // column `lane` of (s + Dd^-1)^-1 s
+    // Q = 0.5 diag(1/(p_a+p_b)) Y, symmetrised:  Qraw[i][lane] = 0.5 dinv[i] y[i]
+    if (lane < DP) {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = 0.5 * dinv[i] * y[i];
     }
-    __syncthreads();
-    if (tid == 0 && !sok && p.info) atomicOr(&p.info[r], 1);
-    // Q = 0.5 R^-1 s = 0.5 diag(1/(p_a+p_b)) (s+Dd^-1)^-1 s, symmetrised into sA
-    for (int e = tid; e < DP * DP; e += blockDim.x) {
-        const int i = e / DP, j = e % DP;
-        const double qi = sdinv[i] * sB[i * SLD + j];
-        const double qj = sdinv[j] * sB[j * SLD + i];
-        sA[i * SLD + j] = 0.25 * (qi + qj);
+    double ldet = 0.0;
+#pragma unroll
+    for (int j = 0; j < DP; ++j) ldet += 2.0 * log(Ls[j * SLD + j]);
+    for (int d = 0; d < D; ++d) ldet += log(pa[d] + pb[d]);    // log det R_ab
+    __syncwarp();
+    double qsym[DP];
+#pragma unroll
+    for (int i = 0; i < DP; ++i) qsym[i] = 0.5 * (Qs[i * SLD + li] + Qs[li * SLD + i]);
+    __syncwarp();
+    if (lane < DP) {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = qsym[i];
     }
-    __syncthreads();
+    if (lane == 0 && !ok && p.info) atomicOr(&p.info[r], 1);
+    __syncwarp();
     if (BWD) {
         double* Qo = wsr + p.oQ + (size_t)q * D * D;
         double* Co = wsr + p.oC + (size_t)q * D * D;
-        for (int e = tid; e < D * D; e += blockDim.x) {
-            const int i = e / D, j = e % D;
-            Qo[e] = sA[i * SLD + j];
-            Co[e] = 0.5 * (sC[i * SLD + j] + sC[j * SLD + i]);
+        double c[DP];
+#pragma unroll
+        for (int i = 0; i < DP; ++i) c[i] = (i == li) ? 1.0 : 0.0;
+        chol_solve_regs<DP>(Ls, c);                            // column `lane` of C = (s + Dd^-1)^-1 (symmetric)
+        if (lane < D) {
+#pragma unroll
+            for (int i = 0; i < DP; ++i)
+                if (i < D) { Qo[i * D + lane] = qsym[i]; Co[i * D + lane] = c[i]; }
         }
-        if (tid == 0) wsr[p.oLd + q] = slogdet;
+        if (lane == 0) wsr[p.oLd + q] = ldet;
     }
     const double lsa = log(sf2[a]), lsb = log(sf2[b]);
-    const double hld = 0.5 * slogdet;
-    for (int nn = tid; nn < np; nn += blockDim.x) {
+    const double hld = 0.5 * ldet;
+    for (int nn = lane; nn < np; nn += 32) {
         double Apv = NEG_PAD, Bqv = NEG_PAD;
         double u[DP];
 #pragma unroll
@@ -219,7 +283,7 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
                 z[d] = d < D ? X[(size_t)nn * D + d] - sm[d] : 0.0;
-                za[d] = spa[d] * z[d]; zb[d] = spb[d] * z[d];
+                za[d] = pa[d] * z[d]; zb[d] = pb[d] * z[d];
                 ka = fma(-0.5 * za[d], z[d], ka);
                 kb = fma(-0.5 * zb[d], z[d], kb);
             }
@@ -229,13 +293,13 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
                 double va = 0.0, vb = 0.0;
 #pragma unroll
                 for (int j = 0; j < DP; ++j) {
-                    const double qij = sA[i * SLD + j];
+                    const double qij = Qs[i * SLD + j];
                     va = fma(qij, za[j], va);
                     vb = fma(qij, zb[j], vb);
                 }
                 qa = fma(za[i], va, qa);
                 qb = fma(zb[i], vb, qb);
-                u[i] = 2.0 * spb[i] * va;                        // U' = p_b o (2 Q z_a)
+                u[i] = 2.0 * pb[i] * va;                       // U' = p_b o (2 Q z_a)
             }
             Apv = ka + qa - hld;
             Bqv = kb + qb;
@@ -257,101 +321,123 @@ __global__ void __launch_bounds__(128) mm_setup_kernel(MMParams p) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// tile kernel
+// tile kernel: CTA = (row block of 64 centres, restart, pair slice).  zeta (all columns) is staged ONCE per
+// CTA in shared memory by a TMA bulk copy; the CTA then loops over its pairs q = y, y+S, ...; the small
+// per-pair column vectors B_q[m], beta_b[m] are read through the read-only L1 path, the per-pair row
+// operands (U' fragments, A', beta_a) are prefetched one pair ahead.  Every warp writes its own partial
+// T_ab (no block barrier per pair); mm_finish sums them in fixed order.
 // -------------------------------------------------------------------------------------------------
 static inline __host__ __device__ size_t mm_tile_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
-    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
+    return (size_t)cm * ldz * 8 + EXP_TAB * 8 + 16;
 }
+static inline __host__ __device__ int mm_tile_nchunks(int np) { return (np + TILE_CM - 1) / TILE_CM; }
+// number of per-pair partial slots written by the tile kernel
+static inline __host__ __device__ int mm_tile_slots(int np) { return (np / 64) * 8 * mm_tile_nchunks(np); }
 
 template <int KS>
-__global__ void __launch_bounds__(256, 2) mm_tile_kernel(MMParams p) {
+__global__ void __launch_bounds__(256, 2) mm_tile_kernel(MMParams p, int S) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMWs& L = p.L;
-    const int np = L.np, ldz = L.ldz;
+    const int np = L.np, ldz = L.ldz, n = p.gp.n;
     const int CM = np < TILE_CM ? np : TILE_CM;
+    const int nchunks = mm_tile_nchunks(np);
     double* sZ = reinterpret_cast<double*>(smem_raw);
-    double* sBq = sZ + (size_t)CM * ldz;
-    double* sBe = sBq + CM;
-    double* tab = sBe + CM;
+    double* tab = sZ + (size_t)CM * ldz;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
 
-    const int r = blockIdx.z, q = blockIdx.y, rb = blockIdx.x;
-    int a, b;
-    pair_decode(q, a, b);
+    const int r = blockIdx.z, y = blockIdx.y, rb = blockIdx.x;
     const double* wsr = p.ws + (size_t)r * L.per_r;
+    double* Tp = p.ws + (size_t)r * L.per_r + L.Tpart;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = rb * 64 + warp * 8;
     const int row = row0 + g;
-    const bool active = row0 < p.gp.n;                 // warp-uniform
-
-    double ua[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)q * np + row) * ldz + 4 * ks + t];
-    const double Apv = wsr[L.Ap + (size_t)q * np + row];
-    const double ba = wsr[L.betap + (size_t)a * np + row];
-    const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
-    const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+    const bool active = row0 < n;                       // warp-uniform
+    const int slots = L.NB * 8 * nchunks;
+    const int ncol8 = (n + 7) & ~7;                     // columns beyond this are pure padding
 
     exp_table_init(tab);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
 
-    double acc = 0.0, tr = 0.0;
     unsigned phase = 0;
-    for (int c0 = 0; c0 < np; c0 += CM) {
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * CM;
         const int cm = (np - c0) < CM ? (np - c0) : CM;
+        const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;      // valid columns in this chunk (multiple of 8)
+        if (ch > 0) __syncthreads();
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16));
+            mbar_expect_tx(bar, (unsigned)(cm * ldz * 8));
             tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
-            tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
-            tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
+        }
+        // prefetch the row operands of the first pair while the copy is in flight
+        double ua[KS], Apv = 0.0, ba = 0.0;
+        if (y < L.P) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)y * np + row) * ldz + 4 * ks + t];
+            Apv = wsr[L.Ap + (size_t)y * np + row];
         }
         mbar_wait(bar, phase);
         phase ^= 1;
-        if (active) {
-            for (int cg = 0; cg < cm; cg += 32) {
-                double2 ik[4];
-                if (diag) {
+        for (int q = y; q < L.P; q += S) {
+            int a, b;
+            pair_decode(q, a, b);
+            ba = wsr[L.betap + (size_t)a * np + row];
+            const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
+            const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk + c0 : nullptr;
+            const double* Bq = wsr + L.Bq + (size_t)q * np + c0;
+            const double* Be = wsr + L.betap + (size_t)b * np + c0;
+            // row operands of the next pair (prefetch)
+            const int qn = q + S;
+            double uan[KS], Apn = 0.0;
+            if (qn < L.P) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        ik[j] = *reinterpret_cast<const double2*>(ikrow + c0 + cg + 8 * j + 2 * t);
-                }
+                for (int ks = 0; ks < KS; ++ks) uan[ks] = wsr[L.U + ((size_t)qn * np + row) * ldz + 4 * ks + t];
+                Apn = wsr[L.Ap + (size_t)qn * np + row];
+            }
+            double acc = 0.0, tr = 0.0;
+            if (active) {
+                for (int cg = 0; cg < cend; cg += 32) {
+                    double2 ik[4], bq[4], bb[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int col = cg + 8 * j;
-                    const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
-                    double e0 = Apv + bq.x, e1 = Apv + bq.y;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
-                        dmma884(e0, e1, ua[ks], bf);
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = cg + 8 * j + 2 * t;
+                        const bool v = (cg + 8 * j) < cend;
+                        bq[j] = v ? __ldg(reinterpret_cast<const double2*>(Bq + col)) : make_double2(NEG_PAD, NEG_PAD);
+                        bb[j] = v ? __ldg(reinterpret_cast<const double2*>(Be + col)) : make_double2(0.0, 0.0);
+                        if (diag) ik[j] = v ? __ldg(reinterpret_cast<const double2*>(ikrow + col)) : make_double2(0.0, 0.0);
                     }
-                    const double l0 = exp_tab(e0, tab), l1 = exp_tab(e1, tab);
-                    const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
-                    acc = fma(bb.x, l0, acc);
-                    acc = fma(bb.y, l1, acc);
-                    if (diag) { tr = fma(ik[j].x, l0, tr); tr = fma(ik[j].y, l1, tr); }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = cg + 8 * j;
+                        if (col < cend) {                                   // warp-uniform
+                            double e0 = Apv + bq[j].x, e1 = Apv + bq[j].y;
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) {
+                                const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
+                                dmma884(e0, e1, ua[ks], bf);
+                            }
+                            const double l0 = exp_tab(e0, tab), l1 = exp_tab(e1, tab);
+                            acc = fma(bb[j].x, l0, acc);
+                            acc = fma(bb[j].y, l1, acc);
+                            if (diag) { tr = fma(ik[j].x, l0, tr); tr = fma(ik[j].y, l1, tr); }
+                        }
+                    }
                 }
             }
+            // row sums -> beta_a-weighted total of this warp's 8 rows
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            double v = (t == 0) ? ba * acc : 0.0;
+            v = warp_sum(v);
+            tr = warp_sum(tr);
+            if (lane == 0) Tp[(size_t)q * slots + ((size_t)rb * 8 + warp) * nchunks + ch] = active ? (v - tr) : 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) ua[ks] = uan[ks];
+            Apv = Apn;
         }
-        __syncthreads();
-    }
-    // row sums -> beta_a-weighted total
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    double v = (t == 0) ? ba * acc : 0.0;
-    v = warp_sum(v);
-    tr = warp_sum(tr);
-    __shared__ double sred[8];
-    if (lane == 0) sred[warp] = active ? (v - tr) : 0.0;
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < 8; ++w) tot += sred[w];
-        p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * L.NB + rb] = tot;
     }
 }
 
@@ -368,7 +454,8 @@ __device__ __forceinline__ void mm_finish_device(const MMParams& p, int r) {
         int a, b;
         pair_decode(q, a, b);
         double T = 0.0;
-        for (int k = 0; k < L.NB; ++k) T += wsr[L.Tpart + (size_t)q * L.NB + k];
+        const int slots = mm_tile_slots(L.np);
+        for (int k = 0; k < slots; ++k) T += wsr[L.Tpart + (size_t)q * slots + k];
         const double Ma = p.M[(size_t)r * E + a], Mb = p.M[(size_t)r * E + b];
         double v = T - Ma * Mb;
         if (a == b) v += (gp.mode == 0) ? sf2[a] : 1e-6;

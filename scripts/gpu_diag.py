@@ -31,10 +31,10 @@ for which in range(5):
     if which == 0:
         rec["TFLOPS"] = 2 * thread_ops / t / 1e12
     elif which == 1:
-        rec["TFLOPS"] = 2 * (blocks * 8 * iters * 8.0) * 256 / t / 1e12      # 8 DMMA/warp/iter x 256 FMA
+        rec["TFLOPS"] = 2 * (blocks * 8 * iters * 16.0) * 256 / t / 1e12     # 16 DMMA/warp/iter x 256 FMA
     elif which == 2:
         rec["dfma_TFLOPS"] = 2 * thread_ops / t / 1e12
-        rec["dmma_TFLOPS"] = 2 * (blocks * 8 * iters * 8.0) * 256 / t / 1e12
+        rec["dmma_TFLOPS"] = 2 * (blocks * 8 * iters * 16.0) * 256 / t / 1e12
     else:
         rec["Gexp_per_s"] = thread_ops / t / 1e9
     out[names[which]] = rec
