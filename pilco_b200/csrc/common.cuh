@@ -19,7 +19,7 @@
 #define MAXD PILCO_MAX_D
 #define MAXE PILCO_MAX_E
 #define SLD  17                 // leading dimension of small smem matrices (odd -> conflict-light)
-#define NEG_PAD (-1.0e5)        // exponent value for padded rows/cols: exp() clamps it to ~1e-304
+#define NEG_PAD (-1.0e9)        // (scaled) exponent of padded rows/cols: exp_scaled() clamps it to ~1e-304
 
 #define CUDA_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return PILCO_ERR_LAUNCH; } while (0)
 
@@ -180,18 +180,10 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 // |r| <= ln2/128 so a degree-5 expm1 polynomial is exact to < 1e-16 relative.  10 fp64-pipe
 // instructions + one shared-memory table read; arguments below -700 are clamped (result ~1e-304).
 // ---------------------------------------------------------------------------------------------
-#ifndef EXP_TAB
-#define EXP_TAB 256             // 64 -> degree-5 expm1 polynomial, 256 -> degree 4, 2048 -> degree 3
-#endif
-#if EXP_TAB == 64
-#define EXP_SHIFT 6
-#elif EXP_TAB == 256
+#define EXP_TAB 256
 #define EXP_SHIFT 8
-#elif EXP_TAB == 2048
-#define EXP_SHIFT 11
-#else
-#error "EXP_TAB must be 64, 256 or 2048"
-#endif
+#define EXP_SC 369.3299304675746            // EXP_TAB / ln 2: exponents are carried PRE-SCALED by this factor
+#define EXP_CLAMP (-258048.0)               // scaled exponent floor (= -698.7 unscaled), hi word 0xC10F8000
 
 // table T[j] = 2^(j/EXP_TAB), correctly rounded on the host, uploaded once (exp_table_upload)
 // (one copy per translation unit: the library is built without relocatable device code)
@@ -210,44 +202,27 @@ __device__ __forceinline__ void exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = g_exp_tab[j];
 }
 
-__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
-    // clamp very negative arguments with integer ops (keeps the fp64 pipe free)
+// exp(x) for a PRE-SCALED argument xs = x * EXP_SC (the setup kernels fold EXP_SC into A', B, U', so the DMMA
+// delivers xs directly):  xs = 256 k + j + r',  exp(x) = 2^k T[j] exp(r' ln2/256),  |r'| <= 1/2.
+// 8 fp64-pipe instructions (3 add, 3 fma, 1 mul, 1 fma) + integer ops + one shared-memory table read.
+__device__ __forceinline__ double exp_scaled(double xs, const double* __restrict__ tab) {
     {
-        const unsigned hi = (unsigned)__double2hiint(x);
-        if (hi > 0xC085E000u) x = -700.0;                 // x < -700 (or negative NaN)
+        const unsigned hi = (unsigned)__double2hiint(xs);
+        if (hi > 0xC10F8000u) xs = EXP_CLAMP;             // xs < -258048 (or negative NaN): result ~1e-304
     }
     const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
-#if EXP_TAB == 64
-    const double t  = fma(x, 92.33248261689366, MAGIC);   // x * 64/ln2, rounded to integer in the low bits
+    const double t  = xs + MAGIC;                         // round to integer in the low mantissa bits
+    const int    ki = __double2loint(t);
     const double kd = t - MAGIC;
-    double r = fma(kd, -0.010830424696249145, x);         // Cody-Waite: ln2/64 = C1 + C2
-    r = fma(kd, -3.623510646634843e-19, r);
-    double q = 0.008333333333333333;                      // expm1(r)/r, degree 4 in r
-    q = fma(q, r, 0.041666666666666664);
-#elif EXP_TAB == 256
-    const double t  = fma(x, 369.3299304675746, MAGIC);   // x * 256/ln2
-    const double kd = t - MAGIC;
-    double r = fma(kd, -0.0027076061740622863, x);        // ln2/256 = C1 + C2
-    r = fma(kd, -9.058776616587108e-20, r);
-    double q = 0.041666666666666664;                      // |r| <= ln2/512: r^5/120 < 4e-17
-#else
-    const double t  = fma(x, 2954.639443740597, MAGIC);   // x * 2048/ln2
-    const double kd = t - MAGIC;
-    double r = fma(kd, -0.00033845077175778579, x);       // ln2/2048 = C1 + C2
-    r = fma(kd, -1.1323470770733885e-20, r);
-    double q = 0.16666666666666666;                       // |r| <= ln2/4096: r^4/24 < 4e-17
-#endif
-    const int ki = __double2loint(t);
-#if EXP_TAB != 2048
-    q = fma(q, r, 0.16666666666666666);
-#endif
-    q = fma(q, r, 0.5);
-    q = fma(q, r, 1.0);
+    const double r  = xs - kd;                            // exact, in [-1/2, 1/2]
+    double q = 2.239395190875157e-12;                     // (ln2/256)^k / k!, k = 4..1
+    q = fma(q, r, 3.3083026805413713e-09);
+    q = fma(q, r, 3.6655655969101062e-06);
+    q = fma(q, r, 0.0027076061740622863);
     const double tj = tab[ki & (EXP_TAB - 1)];
-    const double em1 = q * r;
-    const double v = fma(tj, em1, tj);                    // T[j] * exp(r), in [1, 2.01)
-    // scale by 2^k: add k to the exponent field (k >= -1011 after the clamp, v normal)
-    const int k = ki >> EXP_SHIFT;
+    const double em1 = q * r;                             // expm1(r ln2/256), |.| < 1.36e-3
+    const double v = fma(tj, em1, tj);                    // T[j] * exp(.), in [1, 2.01)
+    const int k = ki >> EXP_SHIFT;                        // k >= -1008 after the clamp, v normal
     return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
 }
 

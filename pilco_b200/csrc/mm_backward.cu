@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
                     const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
                     dmma884(e0, e1, ua[ks], bf);
                 }
-                const double l0 = exp_tab(e0, tab), l1 = exp_tab(e1, tab);
+                const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
                 const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                 const double w0 = bb.x * l0, w1 = bb.y * l1;
                 const double* z0 = sZ + (size_t)(col + 2 * t) * ldz;

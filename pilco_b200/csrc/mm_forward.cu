@@ -1,4 +1,5 @@
 // mm_forward.cu -- host side of pilco_mm_forward (C ABI) + shared launcher.
+#include <stdlib.h>
 #include "mm_kernels.cuh"
 
 int mm_check_model(const pilco_gp_model* gp) {
@@ -12,29 +13,24 @@ int mm_check_model(const pilco_gp_model* gp) {
     return PILCO_OK;
 }
 
-// pair slices per (row block, restart): enough CTAs for >= ~3 resident waves of 2 CTAs/SM, at most P
-static int tile_slices(const MMParams& p) {
-    const long long base = (long long)p.L.NB * p.R;
-    long long S = (148LL * 2 * 3 + base - 1) / base;
-    if (S > p.L.P) S = p.L.P;
-    if (S < 1) S = 1;
-    return (int)S;
-}
-
 template <int KS>
 static int launch_tile(const MMParams& p, cudaStream_t st) {
-    const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
     static bool configured = false;
+    static int variant = 1;          // 0: 2 CTAs/SM (<=128 regs), 1: 3 CTAs/SM (<=85 regs)
     if (!configured) {
-        if (cudaFuncSetAttribute(mm_tile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)mm_tile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        const char* e = getenv("PILCO_TILE_VARIANT");       // tuning switch
+        if (e && e[0] >= '0' && e[0] <= '1') variant = e[0] - '0';
+        const int big = (int)mm_tile_smem_bytes(TILE_CM, 20);
+        if (cudaFuncSetAttribute(mm_tile_kernel<KS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(mm_tile_kernel<KS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }
     int rc = exp_table_upload();
     if (rc) return rc;
-    const int S = tile_slices(p);
-    dim3 grid(p.L.NB, S, p.R);
-    mm_tile_kernel<KS><<<grid, 256, smem, st>>>(p, S);
+    const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
+    dim3 grid(p.L.NB, p.L.P, p.R);
+    if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p);
+    else mm_tile_kernel<KS, 2><<<grid, 256, smem, st>>>(p);
     return PILCO_OK;
 }
 

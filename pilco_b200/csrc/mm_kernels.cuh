@@ -28,7 +28,7 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     L.Ap = o;    o += (size_t)L.P * L.np;
     L.Bq = o;    o += (size_t)L.P * L.np;
     L.U = o;     o += (size_t)L.P * L.np * L.ldz;
-    L.Tpart = o; o += (size_t)L.P * (L.np / 64) * 8 * ((L.np + TILE_CM - 1) / TILE_CM);
+    L.Tpart = o; o += (size_t)L.P * L.NB;
     L.per_r = (o + 1) & ~(size_t)1;
     return L;
 }
@@ -58,17 +58,18 @@ struct MMParams {
 // -------------------------------------------------------------------------------------------------
 #define SETUP_WARPS 4
 
-// lane i (< DP) holds row i of the SPD matrix in a[0..DP); on exit row i of its lower Cholesky factor.
-// Returns false if a pivot is not positive (all lanes agree).
+// lane i (< DP) holds row i of the SPD matrix in a[0..DP); on exit row i of its lower Cholesky factor, with the
+// INVERSE pivots 1/L[j][j] in ipd[j] (same value in every lane).  Returns false if a pivot is not positive.
 template <int DP>
-__device__ __forceinline__ bool chol_regs(double (&a)[DP], int lane) {
+__device__ __forceinline__ bool chol_regs(double (&a)[DP], double (&ipd)[DP], int lane) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < DP; ++j) {
         double d = __shfl_sync(0xffffffffu, a[j], j);
         if (!(d > 0.0)) { ok = false; d = 1.0; }
-        const double piv = sqrt(d);
-        const double lij = (lane == j) ? piv : a[j] / piv;
+        const double ip = rsqrt(d);
+        ipd[j] = ip;
+        const double lij = (lane == j) ? d * ip : a[j] * ip;
         a[j] = lij;
 #pragma unroll
         for (int k = j + 1; k < DP; ++k) {
@@ -79,27 +80,28 @@ __device__ __forceinline__ bool chol_regs(double (&a)[DP], int lane) {
     return ok;
 }
 
-// Solve (L L^T) x = y for the right-hand side held in y[0..DP) (one per lane); L in shared memory [DP][SLD].
+// Solve (L L^T) x = y for the right-hand side held in y[0..DP) (one per lane); L in shared memory [DP][SLD],
+// inverse pivots in ipd.
 template <int DP>
-__device__ __forceinline__ void chol_solve_regs(const double* __restrict__ Ls, double (&y)[DP]) {
+__device__ __forceinline__ void chol_solve_regs(const double* __restrict__ Ls, const double (&ipd)[DP], double (&y)[DP]) {
 #pragma unroll
     for (int i = 0; i < DP; ++i) {
         double v = y[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) v = fma(-Ls[i * SLD + k], y[k], v);
-        y[i] = v / Ls[i * SLD + i];
+        y[i] = v * ipd[i];
     }
 #pragma unroll
     for (int i = DP - 1; i >= 0; --i) {
         double v = y[i];
 #pragma unroll
         for (int k = i + 1; k < DP; ++k) v = fma(-Ls[k * SLD + i], y[k], v);
-        y[i] = v / Ls[i * SLD + i];
+        y[i] = v * ipd[i];
     }
 }
 
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) {
+__global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams p) {
     const int r = blockIdx.y;
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
         double arow[DP];
 #pragma unroll
         for (int j = 0; j < DP; ++j) arow[j] = s_s[li * SLD + j] + (j == li ? pa[li] : 0.0);
-        const bool ok = chol_regs<DP>(arow, lane);
+        double ipd[DP];
+        const bool ok = chol_regs<DP>(arow, ipd, lane);
         if (lane < DP) {
 #pragma unroll
             for (int j = 0; j < DP; ++j) Ls[lane * SLD + j] = arow[j];
@@ -156,16 +159,16 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
         double y[DP];
 #pragma unroll
         for (int i = 0; i < DP; ++i) y[i] = (i == li) ? 1.0 : 0.0;
-        chol_solve_regs<DP>(Ls, y);                            // column `lane` of W = (s + Lambda^2)^-1
+        chol_solve_regs<DP>(Ls, ipd, y);                       // column `lane` of W = (s + Lambda^2)^-1
         if (lane < DP) {
 #pragma unroll
             for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = y[i];
         }
-        double ld = 0.0, sl = 0.0;
+        double pip = 1.0, pl = 1.0;                            // prod 1/L_jj, prod ell_d^2 (D <= 16: no overflow)
 #pragma unroll
-        for (int j = 0; j < DP; ++j) ld += log(Ls[j * SLD + j]);
-        for (int d = 0; d < D; ++d) sl += log(pa[d]);
-        const double c = exp(log(sf2[a]) + 0.5 * sl - ld);     // sf2 sqrt(prod ell^2 / det(s + Lambda^2))
+        for (int j = 0; j < DP; ++j) pip *= ipd[j];
+        for (int d = 0; d < D; ++d) pl *= pa[d];
+        const double c = sf2[a] * sqrt(pl) * pip;              // sf2 sqrt(prod ell^2 / det(s + Lambda^2))
         if (lane == 0 && !ok && p.info) atomicOr(&p.info[r], 1);
         __syncwarp();
 
@@ -226,7 +229,8 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
     double arow[DP];
 #pragma unroll
     for (int j = 0; j < DP; ++j) arow[j] = s_s[li * SLD + j] + (j == li ? (li < D ? dinv[li] : 1.0) : 0.0);
-    const bool ok = chol_regs<DP>(arow, lane);
+    double ipd[DP];
+    const bool ok = chol_regs<DP>(arow, ipd, lane);
     if (lane < DP) {
 #pragma unroll
         for (int j = 0; j < DP; ++j) Ls[lane * SLD + j] = arow[j];
@@ -235,16 +239,17 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
     double y[DP];
 #pragma unroll
     for (int i = 0; i < DP; ++i) y[i] = s_s[i * SLD + li];     // column `lane` of s
-    chol_solve_regs<DP>(Ls, y);                                // column `lane` of (s + Dd^-1)^-1 s
+    chol_solve_regs<DP>(Ls, ipd, y);                           // column `lane` of (s + Dd^-1)^-1 s
     // Q = 0.5 diag(1/(p_a+p_b)) Y, symmetrised:  Qraw[i][lane] = 0.5 dinv[i] y[i]
     if (lane < DP) {
 #pragma unroll
         for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = 0.5 * dinv[i] * y[i];
     }
-    double ldet = 0.0;
+    double pip = 1.0, pdl = 1.0;
 #pragma unroll
-    for (int j = 0; j < DP; ++j) ldet += 2.0 * log(Ls[j * SLD + j]);
-    for (int d = 0; d < D; ++d) ldet += log(pa[d] + pb[d]);    // log det R_ab
+    for (int j = 0; j < DP; ++j) pip *= ipd[j];
+    for (int d = 0; d < D; ++d) pdl *= (pa[d] + pb[d]);
+    const double ldet = log(pdl) - 2.0 * log(pip);             // log det R_ab = log det(s+Dd^-1) + sum log delta
     __syncwarp();
     double qsym[DP];
 #pragma unroll
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
         double c[DP];
 #pragma unroll
         for (int i = 0; i < DP; ++i) c[i] = (i == li) ? 1.0 : 0.0;
-        chol_solve_regs<DP>(Ls, c);                            // column `lane` of C = (s + Dd^-1)^-1 (symmetric)
+        chol_solve_regs<DP>(Ls, ipd, c);                       // column `lane` of C = (s + Dd^-1)^-1 (symmetric)
         if (lane < D) {
 #pragma unroll
             for (int i = 0; i < DP; ++i)
@@ -272,37 +277,45 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
     }
     const double lsa = log(sf2[a]), lsb = log(sf2[b]);
     const double hld = 0.5 * ldet;
+    // Qa = Q diag(p_a) -> Qs, Qb = Q diag(p_b) -> Ls (L no longer needed): the centre loop then works on z directly
+    __syncwarp();
+    if (lane < DP) {
+#pragma unroll
+        for (int i = 0; i < DP; ++i) { Qs[i * SLD + lane] = qsym[i] * pa[lane]; Ls[i * SLD + lane] = qsym[i] * pb[lane]; }
+    }
+    __syncwarp();
     for (int nn = lane; nn < np; nn += 32) {
         double Apv = NEG_PAD, Bqv = NEG_PAD;
         double u[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) u[d] = 0.0;
         if (nn < n) {
-            double z[DP], za[DP], zb[DP];
+            double z[DP];
             double ka = lsa, kb = lsb;
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
                 z[d] = d < D ? X[(size_t)nn * D + d] - sm[d] : 0.0;
-                za[d] = pa[d] * z[d]; zb[d] = pb[d] * z[d];
-                ka = fma(-0.5 * za[d], z[d], ka);
-                kb = fma(-0.5 * zb[d], z[d], kb);
+                const double z2 = z[d] * z[d];
+                ka = fma(-0.5 * pa[d], z2, ka);
+                kb = fma(-0.5 * pb[d], z2, kb);
             }
             double qa = 0.0, qb = 0.0;
 #pragma unroll
             for (int i = 0; i < DP; ++i) {
-                double va = 0.0, vb = 0.0;
+                double va = 0.0, vb = 0.0;                     // (Q z_a)[i], (Q z_b)[i]
 #pragma unroll
                 for (int j = 0; j < DP; ++j) {
-                    const double qij = Qs[i * SLD + j];
-                    va = fma(qij, za[j], va);
-                    vb = fma(qij, zb[j], vb);
+                    va = fma(Qs[i * SLD + j], z[j], va);
+                    vb = fma(Ls[i * SLD + j], z[j], vb);
                 }
-                qa = fma(za[i], va, qa);
-                qb = fma(zb[i], vb, qb);
+                qa = fma(pa[i] * z[i], va, qa);
+                qb = fma(pb[i] * z[i], vb, qb);
                 u[i] = 2.0 * pb[i] * va;                       // U' = p_b o (2 Q z_a)
             }
-            Apv = ka + qa - hld;
-            Bqv = kb + qb;
+            Apv = EXP_SC * (ka + qa - hld);                     // exponents are stored pre-scaled (exp_scaled)
+            Bqv = EXP_SC * (kb + qb);
+#pragma unroll
+            for (int i = 0; i < DP; ++i) u[i] *= EXP_SC;
         }
         if (BWD) {
             if (b == 0) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
@@ -321,123 +334,151 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup_kernel(MMParams p) 
 }
 
 // -------------------------------------------------------------------------------------------------
-// tile kernel: CTA = (row block of 64 centres, restart, pair slice).  zeta (all columns) is staged ONCE per
-// CTA in shared memory by a TMA bulk copy; the CTA then loops over its pairs q = y, y+S, ...; the small
-// per-pair column vectors B_q[m], beta_b[m] are read through the read-only L1 path, the per-pair row
-// operands (U' fragments, A', beta_a) are prefetched one pair ahead.  Every warp writes its own partial
-// T_ab (no block barrier per pair); mm_finish sums them in fixed order.
+// tile kernel: CTA = (row block of 64 centres, pair, restart), 8 warps x 8 rows.  The column operands
+// (zeta [cols, ldz], B_q, beta_b) are staged in shared memory by TMA bulk copies; each warp sweeps all
+// (valid) columns in groups of 4 DMMA tiles.  Diagonal pairs (a == b) exploit the symmetry of
+// G[n,m] L'[n,m]: only column tiles at or right of the row tile are visited, strictly-upper tiles count twice.
 // -------------------------------------------------------------------------------------------------
 static inline __host__ __device__ size_t mm_tile_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
-    return (size_t)cm * ldz * 8 + EXP_TAB * 8 + 16;
+    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
 }
-static inline __host__ __device__ int mm_tile_nchunks(int np) { return (np + TILE_CM - 1) / TILE_CM; }
-// number of per-pair partial slots written by the tile kernel
-static inline __host__ __device__ int mm_tile_slots(int np) { return (np / 64) * 8 * mm_tile_nchunks(np); }
+static inline __host__ __device__ int mm_tile_slots(int np) { return np / 64; }
 
-template <int KS>
-__global__ void __launch_bounds__(256, 2) mm_tile_kernel(MMParams p, int S) {
+template <int KS, int MINB>
+__global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMWs& L = p.L;
     const int np = L.np, ldz = L.ldz, n = p.gp.n;
     const int CM = np < TILE_CM ? np : TILE_CM;
-    const int nchunks = mm_tile_nchunks(np);
     double* sZ = reinterpret_cast<double*>(smem_raw);
-    double* tab = sZ + (size_t)CM * ldz;
+    double* sBq = sZ + (size_t)CM * ldz;
+    double* sBe = sBq + CM;
+    double* tab = sBe + CM;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
 
-    const int r = blockIdx.z, y = blockIdx.y, rb = blockIdx.x;
+    const int r = blockIdx.z, q = blockIdx.y, rb = blockIdx.x;
+    int a, b;
+    pair_decode(q, a, b);
     const double* wsr = p.ws + (size_t)r * L.per_r;
-    double* Tp = p.ws + (size_t)r * L.per_r + L.Tpart;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = rb * 64 + warp * 8;
     const int row = row0 + g;
-    const bool active = row0 < n;                       // warp-uniform
-    const int slots = L.NB * 8 * nchunks;
-    const int ncol8 = (n + 7) & ~7;                     // columns beyond this are pure padding
+    const bool active = row0 < n;                      // warp-uniform
+    const int ncol8 = (n + 7) & ~7;                    // columns at or beyond this are pure padding
+    const bool sympair = (a == b);                     // symmetric pair: visit the upper triangle only
+    const bool diag = sympair && (p.gp.mode == 0) && (p.gp.iK != nullptr);
+    // first column this CTA needs (symmetric pairs skip everything left of its first row tile)
+    const int cfirst = sympair ? rb * 64 : 0;
 
-    exp_table_init(tab);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    exp_table_init(tab);
+    double ua[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)q * np + row) * ldz + 4 * ks + t];
+    const double Apv = wsr[L.Ap + (size_t)q * np + row];
+    const double ba = wsr[L.betap + (size_t)a * np + row];
+    const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
     __syncthreads();
 
+    double acc2 = 0.0, accd = 0.0, tr2 = 0.0, trd = 0.0;   // strictly-upper / diagonal-tile accumulators
     unsigned phase = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int c0 = ch * CM;
+    for (int c0 = (cfirst / CM) * CM; c0 < ncol8; c0 += CM) {
+        const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
         const int cm = (np - c0) < CM ? (np - c0) : CM;
-        const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;      // valid columns in this chunk (multiple of 8)
-        if (ch > 0) __syncthreads();
+        const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;        // chunk-local end of valid columns
+        const int ncopy = cm - lo;
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)(cm * ldz * 8));
-            tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
-        }
-        // prefetch the row operands of the first pair while the copy is in flight
-        double ua[KS], Apv = 0.0, ba = 0.0;
-        if (y < L.P) {
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)y * np + row) * ldz + 4 * ks + t];
-            Apv = wsr[L.Ap + (size_t)y * np + row];
+            mbar_expect_tx(bar, (unsigned)(ncopy * ldz * 8 + ncopy * 16));
+            tma_bulk_g2s(sZ + (size_t)lo * ldz, wsr + L.zeta + (size_t)(c0 + lo) * ldz, (unsigned)(ncopy * ldz * 8), bar);
+            tma_bulk_g2s(sBq + lo, wsr + L.Bq + (size_t)q * np + c0 + lo, (unsigned)(ncopy * 8), bar);
+            tma_bulk_g2s(sBe + lo, wsr + L.betap + (size_t)b * np + c0 + lo, (unsigned)(ncopy * 8), bar);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
-        for (int q = y; q < L.P; q += S) {
-            int a, b;
-            pair_decode(q, a, b);
-            ba = wsr[L.betap + (size_t)a * np + row];
-            const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
-            const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk + c0 : nullptr;
-            const double* Bq = wsr + L.Bq + (size_t)q * np + c0;
-            const double* Be = wsr + L.betap + (size_t)b * np + c0;
-            // row operands of the next pair (prefetch)
-            const int qn = q + S;
-            double uan[KS], Apn = 0.0;
-            if (qn < L.P) {
+        if (active) {
+            // symmetric pairs start at this warp's own row tile (global column row0)
+            int cstart = lo;
+            if (sympair && row0 > c0 + lo) cstart = (row0 - c0) & ~31;
+            if (cstart < lo) cstart = lo;
+            for (int cg = cstart; cg < cend; cg += 32) {
+                double2 ik[4];
+                if (diag) {
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) uan[ks] = wsr[L.U + ((size_t)qn * np + row) * ldz + 4 * ks + t];
-                Apn = wsr[L.Ap + (size_t)qn * np + row];
-            }
-            double acc = 0.0, tr = 0.0;
-            if (active) {
-                for (int cg = 0; cg < cend; cg += 32) {
-                    double2 ik[4], bq[4], bb[4];
+                    for (int j = 0; j < 4; ++j)
+                        ik[j] = *reinterpret_cast<const double2*>(ikrow + c0 + cg + 8 * j + 2 * t);   // zero padded: always in bounds
+                }
+                // fast path: all four tiles valid and (symmetric pairs) strictly right of the diagonal tile
+                const bool full = (cg + 32 <= cend) && (!sympair || c0 + cg > row0);
+                if (full) {
+                    double e[8];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int col = cg + 8 * j + 2 * t;
-                        const bool v = (cg + 8 * j) < cend;
-                        bq[j] = v ? __ldg(reinterpret_cast<const double2*>(Bq + col)) : make_double2(NEG_PAD, NEG_PAD);
-                        bb[j] = v ? __ldg(reinterpret_cast<const double2*>(Be + col)) : make_double2(0.0, 0.0);
-                        if (diag) ik[j] = v ? __ldg(reinterpret_cast<const double2*>(ikrow + col)) : make_double2(0.0, 0.0);
+                        const double2 bq = *reinterpret_cast<const double2*>(sBq + cg + 8 * j + 2 * t);
+                        e[2 * j] = Apv + bq.x; e[2 * j + 1] = Apv + bq.y;
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double bf = sZ[(size_t)(cg + 8 * j + g) * ldz + 4 * ks + t];
+                            dmma884(e[2 * j], e[2 * j + 1], ua[ks], bf);
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int col = cg + 8 * j;
-                        if (col < cend) {                                   // warp-uniform
-                            double e0 = Apv + bq[j].x, e1 = Apv + bq[j].y;
+                        const double l0 = exp_scaled(e[2 * j], tab), l1 = exp_scaled(e[2 * j + 1], tab);
+                        const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
+                        acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
+                        if (diag) { tr2 = fma(ik[j].x, l0, tr2); tr2 = fma(ik[j].y, l1, tr2); }
+                    }
+                    continue;
+                }
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int col = cg + 8 * j;
+                    const int gcol = c0 + col;
+                    if (col < cend && (!sympair || gcol >= row0)) {         // warp-uniform
+                        const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
+                        double e0 = Apv + bq.x, e1 = Apv + bq.y;
 #pragma unroll
-                            for (int ks = 0; ks < KS; ++ks) {
-                                const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
-                                dmma884(e0, e1, ua[ks], bf);
-                            }
-                            const double l0 = exp_tab(e0, tab), l1 = exp_tab(e1, tab);
-                            acc = fma(bb[j].x, l0, acc);
-                            acc = fma(bb[j].y, l1, acc);
-                            if (diag) { tr = fma(ik[j].x, l0, tr); tr = fma(ik[j].y, l1, tr); }
+                        for (int ks = 0; ks < KS; ++ks) {
+                            const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
+                            dmma884(e0, e1, ua[ks], bf);
+                        }
+                        const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
+                        const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
+                        const double2 ikj = diag ? *reinterpret_cast<const double2*>(ikrow + gcol + 2 * t) : make_double2(0.0, 0.0);
+                        if (sympair && gcol == row0) {
+                            accd = fma(bb.x, l0, accd); accd = fma(bb.y, l1, accd);
+                            trd = fma(ikj.x, l0, trd); trd = fma(ikj.y, l1, trd);
+                        } else {
+                            acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
+                            tr2 = fma(ikj.x, l0, tr2); tr2 = fma(ikj.y, l1, tr2);
                         }
                     }
                 }
             }
-            // row sums -> beta_a-weighted total of this warp's 8 rows
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            double v = (t == 0) ? ba * acc : 0.0;
-            v = warp_sum(v);
-            tr = warp_sum(tr);
-            if (lane == 0) Tp[(size_t)q * slots + ((size_t)rb * 8 + warp) * nchunks + ch] = active ? (v - tr) : 0.0;
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) ua[ks] = uan[ks];
-            Apv = Apn;
         }
+        __syncthreads();
+    }
+    // row sums -> beta_a-weighted total; symmetric pairs: diagonal tile once, strictly-upper tiles twice
+    double acc = sympair ? accd + 2.0 * acc2 : acc2;
+    double tr = sympair ? trd + 2.0 * tr2 : tr2;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    double v = (t == 0) ? ba * acc : 0.0;
+    v = warp_sum(v);
+    tr = warp_sum(tr);
+    __shared__ double sred[8];
+    if (lane == 0) sred[warp] = active ? (v - tr) : 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += sred[w];
+        p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * L.NB + rb] = tot;
     }
 }
 
