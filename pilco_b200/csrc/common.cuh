@@ -206,10 +206,9 @@ __device__ __forceinline__ void exp_table_init(double* tab) {
 // delivers xs directly):  xs = 256 k + j + r',  exp(x) = 2^k T[j] exp(r' ln2/256),  |r'| <= 1/2.
 // 8 fp64-pipe instructions (3 add, 3 fma, 1 mul, 1 fma) + integer ops + one shared-memory table read.
 __device__ __forceinline__ double exp_scaled(double xs, const double* __restrict__ tab) {
-    {
-        const unsigned hi = (unsigned)__double2hiint(xs);
-        if (hi > 0xC10F8000u) xs = EXP_CLAMP;             // xs < -258048 (or negative NaN): result ~1e-304
-    }
+    // clamp xs >= EXP_CLAMP with ONE integer instruction: for negative doubles a larger magnitude is a larger
+    // high word, positive values (high word < 0x80000000) pass unchanged, NaNs propagate
+    xs = __hiloint2double((int)min((unsigned)__double2hiint(xs), 0xC10F8000u), __double2loint(xs));
     const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
     const double t  = xs + MAGIC;                         // round to integer in the low mantissa bits
     const int    ki = __double2loint(t);
@@ -219,11 +218,13 @@ __device__ __forceinline__ double exp_scaled(double xs, const double* __restrict
     q = fma(q, r, 3.3083026805413713e-09);
     q = fma(q, r, 3.6655655969101062e-06);
     q = fma(q, r, 0.0027076061740622863);
-    const double tj = tab[ki & (EXP_TAB - 1)];
+    const double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + ((ki << 3) & ((EXP_TAB - 1) << 3)));
     const double em1 = q * r;                             // expm1(r ln2/256), |.| < 1.36e-3
     const double v = fma(tj, em1, tj);                    // T[j] * exp(.), in [1, 2.01)
-    const int k = ki >> EXP_SHIFT;                        // k >= -1008 after the clamp, v normal
-    return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+    // scale by 2^k, k = ki >> 8 >= -1008 after the clamp (v normal): one shift + one integer multiply-add
+    int hi;
+    asm("mad.lo.s32 %0, %1, 0x100000, %2;" : "=r"(hi) : "r"(ki >> EXP_SHIFT), "r"(__double2hiint(v)));
+    return __hiloint2double(hi, __double2loint(v));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -466,12 +466,11 @@ int mm_backward_launch(MMBwdParams bp, cudaStream_t st) {
     sp.L = bp.B.F; sp.bwd = 1; sp.oQ = bp.B.oQ; sp.oC = bp.B.oC; sp.oLd = bp.B.oLd;
     // per-restart stride of the setup arrays must be the backward stride
     sp.L.per_r = bp.B.per_r;
-    dim3 gs((E * E + SETUP_WARPS - 1) / SETUP_WARPS, R);
     switch (ks) {
-        case 1: mm_setup_kernel<4, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
-        case 2: mm_setup_kernel<8, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
-        case 3: mm_setup_kernel<12, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
-        default: mm_setup_kernel<16, true><<<gs, 32 * SETUP_WARPS, 0, st>>>(sp); break;
+        case 1: mm_setup_launch<4, true>(sp, st); break;
+        case 2: mm_setup_launch<8, true>(sp, st); break;
+        case 3: mm_setup_launch<12, true>(sp, st); break;
+        default: mm_setup_launch<16, true>(sp, st); break;
     }
     CUDA_LAUNCH_CHECK();
     int rc;

@@ -19,30 +19,31 @@ static int launch_tile(const MMParams& p, cudaStream_t st) {
     static int variant = 1;          // 0: 2 CTAs/SM (<=128 regs), 1: 3 CTAs/SM (<=85 regs)
     if (!configured) {
         const char* e = getenv("PILCO_TILE_VARIANT");       // tuning switch
-        if (e && e[0] >= '0' && e[0] <= '1') variant = e[0] - '0';
+        if (e && e[0] >= '0' && e[0] <= '2') variant = e[0] - '0';
         const int big = (int)mm_tile_smem_bytes(TILE_CM, 20);
         if (cudaFuncSetAttribute(mm_tile_kernel<KS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         if (cudaFuncSetAttribute(mm_tile_kernel<KS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(mm_tile_kernel<KS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }
     int rc = exp_table_upload();
     if (rc) return rc;
     const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
     dim3 grid(p.L.NB, p.L.P, p.R);
-    if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p);
+    if (variant == 2) mm_tile_kernel<KS, 4><<<grid, 256, smem, st>>>(p);
+    else if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p);
     else mm_tile_kernel<KS, 2><<<grid, 256, smem, st>>>(p);
     return PILCO_OK;
 }
 
 int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
     const int E = p.gp.E, D = p.gp.D;
-    dim3 gs((E + p.L.P + SETUP_WARPS - 1) / SETUP_WARPS, p.R);
     const int ks = ksteps_of(D);
     switch (ks) {
-        case 1: mm_setup_kernel<4, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        default: mm_setup_kernel<16, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 1: mm_setup_launch<4, false>(p, st); break;
+        case 2: mm_setup_launch<8, false>(p, st); break;
+        case 3: mm_setup_launch<12, false>(p, st); break;
+        default: mm_setup_launch<16, false>(p, st); break;
     }
     CUDA_LAUNCH_CHECK();
     int rc;
@@ -103,13 +104,12 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
     cudaEvent_t ev[4];
     for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
     const int E = gp->E, ks = ksteps_of(gp->D);
-    dim3 gs((E + p.L.P + SETUP_WARPS - 1) / SETUP_WARPS, R);
     cudaEventRecord(ev[0], st);
     switch (ks) {
-        case 1: mm_setup_kernel<4, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        case 2: mm_setup_kernel<8, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        case 3: mm_setup_kernel<12, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
-        default: mm_setup_kernel<16, false><<<gs, 32 * SETUP_WARPS, 0, st>>>(p); break;
+        case 1: mm_setup_launch<4, false>(p, st); break;
+        case 2: mm_setup_launch<8, false>(p, st); break;
+        case 3: mm_setup_launch<12, false>(p, st); break;
+        default: mm_setup_launch<16, false>(p, st); break;
     }
     cudaEventRecord(ev[1], st);
     switch (ks) {

@@ -15,7 +15,7 @@
 #define TILE_CM 512        // columns staged in shared memory per chunk
 
 struct MMWs {            // workspace layout, offsets in doubles relative to the per-restart base
-    size_t zeta, betap, Ap, Bq, U, Tpart, per_r;
+    size_t zeta, betap, Ap, Bq, U, Tpart, Wm, Wc, Qab, Qh, per_r;
     int np, ldz, P, NB;
 };
 
@@ -29,6 +29,11 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     L.Bq = o;    o += (size_t)L.P * L.np;
     L.U = o;     o += (size_t)L.P * L.np * L.ldz;
     L.Tpart = o; o += (size_t)L.P * L.NB;
+    o = (o + 1) & ~(size_t)1;
+    L.Wm = o;    o += (size_t)E * MAXD * MAXD;          // setup stage 1 -> 2: W_a
+    L.Wc = o;    o += (size_t)((E + 1) & ~1);           //                      c_a
+    L.Qab = o;   o += (size_t)L.P * 2 * MAXD * MAXD;    //                      Q diag(p_a), Q diag(p_b)
+    L.Qh = o;    o += (size_t)((L.P + 1) & ~1);         //                      0.5 log det R_ab
     L.per_r = (o + 1) & ~(size_t)1;
     return L;
 }
@@ -100,29 +105,25 @@ __device__ __forceinline__ void chol_solve_regs(const double* __restrict__ Ls, c
     }
 }
 
+// stage 1: the serial part of every task (one warp per task): D x D Cholesky + solves -> matrices in workspace
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams p) {
+__global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p) {
     const int r = blockIdx.y;
     const pilco_gp_model& gp = p.gp;
-    const int n = gp.n, D = gp.D, E = gp.E;
+    const int D = gp.D, E = gp.E;
     const MMWs& L = p.L;
-    const int np = L.np, ldz = L.ldz;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ntask = BWD ? L.P : E + L.P;
     const int task0 = blockIdx.x * SETUP_WARPS + warp;
     const int task = BWD ? task0 + E : task0;                  // BWD: pair tasks only (ordered pairs)
 
     __shared__ double s_s[MAXD * SLD];                         // symmetrised input covariance (all warps)
-    __shared__ double sm[MAXD];
     __shared__ double sLw[SETUP_WARPS][MAXD * SLD];            // per warp: Cholesky factor
-    __shared__ double sQw[SETUP_WARPS][MAXD * SLD];            // per warp: W_a or Q_ab
-    __shared__ double spw[SETUP_WARPS][3][MAXD];               // per warp: p_a / ell^2, p_b, 1/(p_a+p_b)
+    __shared__ double sQw[SETUP_WARPS][MAXD * SLD];            // per warp: raw Q
+    __shared__ double spw[SETUP_WARPS][3][MAXD];
 
-    const double* X = gp.X + (size_t)r * gp.X_bs;
     const double* ell = gp.ell + (size_t)r * gp.ell_bs;
     const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
-    const double* beta = gp.beta + (size_t)r * gp.beta_bs;
-    const double* mr = p.m + (size_t)r * p.m_rs;
     const double* sr = p.s + (size_t)r * p.s_rs;
     double* wsr = p.ws + (size_t)r * L.per_r;
 
@@ -130,7 +131,6 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
         const int i = e / DP, j = e % DP;
         s_s[i * SLD + j] = (i < D && j < D) ? 0.5 * (sr[i * D + j] + sr[j * D + i]) : 0.0;
     }
-    if (tid < DP) sm[tid] = tid < D ? mr[tid] : 0.0;
     __syncthreads();
     if (task0 >= ntask) return;
 
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
     const int li = lane < DP ? lane : DP - 1;                  // clamp so idle lanes read valid memory
 
     if (!BWD && task < E) {
-        // ---------------- output task: mean and input-output covariance of GP a ----------------
+        // ---------------- output task: W_a = (s + Lambda_a^2)^-1 and c_a ----------------
         const int a = task;
         if (lane < DP) { const double l = lane < D ? ell[a * D + lane] : 1.0; pa[lane] = l * l; }
         __syncwarp();
@@ -159,63 +159,24 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
         double y[DP];
 #pragma unroll
         for (int i = 0; i < DP; ++i) y[i] = (i == li) ? 1.0 : 0.0;
-        chol_solve_regs<DP>(Ls, ipd, y);                       // column `lane` of W = (s + Lambda^2)^-1
+        chol_solve_regs<DP>(Ls, ipd, y);                       // column `lane` of W (symmetric)
+        double* Wo = wsr + L.Wm + (size_t)a * MAXD * MAXD;
         if (lane < DP) {
 #pragma unroll
-            for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = y[i];
+            for (int i = 0; i < DP; ++i) Wo[i * DP + lane] = y[i];
         }
         double pip = 1.0, pl = 1.0;                            // prod 1/L_jj, prod ell_d^2 (D <= 16: no overflow)
 #pragma unroll
         for (int j = 0; j < DP; ++j) pip *= ipd[j];
         for (int d = 0; d < D; ++d) pl *= pa[d];
-        const double c = sf2[a] * sqrt(pl) * pip;              // sf2 sqrt(prod ell^2 / det(s + Lambda^2))
-        if (lane == 0 && !ok && p.info) atomicOr(&p.info[r], 1);
-        __syncwarp();
-
-        double acc[DP + 1];
-#pragma unroll
-        for (int i = 0; i <= DP; ++i) acc[i] = 0.0;
-        for (int nn = lane; nn < np; nn += 32) {
-            double z[DP];
-            double bw = 0.0;
-            if (nn < n) {
-#pragma unroll
-                for (int d = 0; d < DP; ++d) z[d] = d < D ? X[(size_t)nn * D + d] - sm[d] : 0.0;
-                double t[DP], e = 0.0;
-#pragma unroll
-                for (int i = 0; i < DP; ++i) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int j = 0; j < DP; ++j) v = fma(Qs[i * SLD + j], z[j], v);
-                    t[i] = v; e = fma(z[i], v, e);
-                }
-                bw = beta[(size_t)a * n + nn];
-                const double w = bw * exp(-0.5 * e);
-                acc[DP] += w;
-#pragma unroll
-                for (int i = 0; i < DP; ++i) acc[i] = fma(w, t[i], acc[i]);
-            } else {
-#pragma unroll
-                for (int d = 0; d < DP; ++d) z[d] = 0.0;
-            }
-            wsr[L.betap + (size_t)a * np + nn] = bw;
-            if (a == 0) {
-                double* zp = wsr + L.zeta + (size_t)nn * ldz;
-#pragma unroll
-                for (int d = 0; d < DP; ++d) zp[d] = z[d];
-                for (int d = DP; d < ldz; ++d) zp[d] = 0.0;
-            }
+        if (lane == 0) {
+            wsr[L.Wc + a] = sf2[a] * sqrt(pl) * pip;           // c_a = sf2 sqrt(prod ell^2 / det(s + Lambda^2))
+            if (!ok && p.info) atomicOr(&p.info[r], 1);
         }
-#pragma unroll
-        for (int i = 0; i <= DP; ++i) acc[i] = warp_sum(acc[i]);
-        if (lane == 0) p.M[(size_t)r * E + a] = c * acc[DP];
-#pragma unroll
-        for (int i = 0; i < DP; ++i)
-            if (lane == i && i < D) p.V[((size_t)r * D + i) * E + a] = c * acc[i];
         return;
     }
 
-    // ---------------- pair task: Q_ab and the per-centre exponent pieces ----------------
+    // ---------------- pair task: Q_ab ----------------
     const int q = task - E;
     int a, b;
     if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);
@@ -240,8 +201,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
 #pragma unroll
     for (int i = 0; i < DP; ++i) y[i] = s_s[i * SLD + li];     // column `lane` of s
     chol_solve_regs<DP>(Ls, ipd, y);                           // column `lane` of (s + Dd^-1)^-1 s
-    // Q = 0.5 diag(1/(p_a+p_b)) Y, symmetrised:  Qraw[i][lane] = 0.5 dinv[i] y[i]
-    if (lane < DP) {
+    if (lane < DP) {                                           // Qraw[i][lane] = 0.5 dinv[i] y[i]
 #pragma unroll
         for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = 0.5 * dinv[i] * y[i];
     }
@@ -254,13 +214,16 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
     double qsym[DP];
 #pragma unroll
     for (int i = 0; i < DP; ++i) qsym[i] = 0.5 * (Qs[i * SLD + li] + Qs[li * SLD + i]);
-    __syncwarp();
+    // stage-2 operands: Qa = Q diag(p_a), Qb = Q diag(p_b) (column `lane`), and 0.5 log det R
+    double* Qo2 = wsr + L.Qab + (size_t)q * 2 * MAXD * MAXD;
     if (lane < DP) {
 #pragma unroll
-        for (int i = 0; i < DP; ++i) Qs[i * SLD + lane] = qsym[i];
+        for (int i = 0; i < DP; ++i) { Qo2[i * DP + lane] = qsym[i] * pa[lane]; Qo2[MAXD * MAXD + i * DP + lane] = qsym[i] * pb[lane]; }
     }
-    if (lane == 0 && !ok && p.info) atomicOr(&p.info[r], 1);
-    __syncwarp();
+    if (lane == 0) {
+        wsr[L.Qh + q] = 0.5 * ldet;
+        if (!ok && p.info) atomicOr(&p.info[r], 1);
+    }
     if (BWD) {
         double* Qo = wsr + p.oQ + (size_t)q * D * D;
         double* Co = wsr + p.oC + (size_t)q * D * D;
@@ -275,16 +238,117 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
         }
         if (lane == 0) wsr[p.oLd + q] = ldet;
     }
-    const double lsa = log(sf2[a]), lsb = log(sf2[b]);
-    const double hld = 0.5 * ldet;
-    // Qa = Q diag(p_a) -> Qs, Qb = Q diag(p_b) -> Ls (L no longer needed): the centre loop then works on z directly
-    __syncwarp();
-    if (lane < DP) {
+}
+
+// stage 2: the throughput part: one CTA (128 threads) per task sweeps the centres
+template <int DP, bool BWD>
+__global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
+    const int r = blockIdx.y;
+    const pilco_gp_model& gp = p.gp;
+    const int n = gp.n, D = gp.D, E = gp.E;
+    const MMWs& L = p.L;
+    const int np = L.np, ldz = L.ldz;
+    const int tid = threadIdx.x;
+    const int task = BWD ? blockIdx.x + E : blockIdx.x;
+
+    __shared__ double sQa[MAXD * MAXD], sQb[MAXD * MAXD];
+    __shared__ double sm[MAXD], pa[MAXD], pb[MAXD];
+    __shared__ __align__(16) double sStage[128 * (MAXD + 5)];   // [128][ldz|1] staging: X block in, U'/zeta block out
+    __shared__ double sred[(MAXD + 1) * 4], sout[MAXD + 1];
+
+    const double* X = gp.X + (size_t)r * gp.X_bs;
+    const double* ell = gp.ell + (size_t)r * gp.ell_bs;
+    const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
+    const double* beta = gp.beta + (size_t)r * gp.beta_bs;
+    const double* mr = p.m + (size_t)r * p.m_rs;
+    double* wsr = p.ws + (size_t)r * L.per_r;
+    if (tid < DP) sm[tid] = tid < D ? mr[tid] : 0.0;
+
+    if (!BWD && task < E) {
+        // ---------------- output task: mean M_a and V_a; betap and zeta ----------------
+        const int a = task;
+        const double* Wg = wsr + L.Wm + (size_t)a * MAXD * MAXD;
+        for (int e = tid; e < DP * DP; e += blockDim.x) sQa[e] = Wg[e];
+        __syncthreads();
+        const double c = wsr[L.Wc + a];
+        double acc[DP + 1];
 #pragma unroll
-        for (int i = 0; i < DP; ++i) { Qs[i * SLD + lane] = qsym[i] * pa[lane]; Ls[i * SLD + lane] = qsym[i] * pb[lane]; }
+        for (int i = 0; i <= DP; ++i) acc[i] = 0.0;
+        const int lds = ldz | 1;
+        for (int n0 = 0; n0 < np; n0 += 128) {
+            const int rows = (n - n0) < 128 ? ((n - n0) > 0 ? (n - n0) : 0) : 128;
+            __syncthreads();
+            for (int e = tid; e < rows * D; e += blockDim.x) sStage[(e / D) * lds + (e % D)] = X[(size_t)n0 * D + e];
+            __syncthreads();
+            const int nn = n0 + tid;
+            double z[DP];
+            double bw = 0.0;
+            if (nn < n) {
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = d < D ? sStage[tid * lds + d] - sm[d] : 0.0;
+                double t[DP], e = 0.0;
+#pragma unroll
+                for (int i = 0; i < DP; ++i) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < DP; ++j) v = fma(sQa[i * DP + j], z[j], v);
+                    t[i] = v; e = fma(z[i], v, e);
+                }
+                bw = beta[(size_t)a * n + nn];
+                const double w = bw * exp(-0.5 * e);
+                acc[DP] += w;
+#pragma unroll
+                for (int i = 0; i < DP; ++i) acc[i] = fma(w, t[i], acc[i]);
+            } else {
+#pragma unroll
+                for (int d = 0; d < DP; ++d) z[d] = 0.0;
+            }
+            if (nn < np) wsr[L.betap + (size_t)a * np + nn] = bw;
+            if (a == 0) {                                       // zeta block: smem -> coalesced double2 stores
+                __syncthreads();
+#pragma unroll
+                for (int d = 0; d < DP; ++d) sStage[tid * lds + d] = z[d];
+                for (int d = DP; d < ldz; ++d) sStage[tid * lds + d] = 0.0;
+                __syncthreads();
+                const int rows_out = (np - n0) < 128 ? (np - n0) : 128;
+                double2* dst = reinterpret_cast<double2*>(wsr + L.zeta + (size_t)n0 * ldz);
+                for (int e = tid; e < rows_out * ldz / 2; e += blockDim.x) {
+                    const int rr = (2 * e) / ldz, cc = (2 * e) % ldz;
+                    dst[e] = make_double2(sStage[rr * lds + cc], sStage[rr * lds + cc + 1]);
+                }
+            }
+        }
+        block_sum<DP + 1>(acc, DP + 1, sred, sout);
+        if (tid == 0) p.M[(size_t)r * E + a] = c * sout[DP];
+        if (tid < D) p.V[((size_t)r * D + tid) * E + a] = c * sout[tid];
+        return;
     }
-    __syncwarp();
-    for (int nn = lane; nn < np; nn += 32) {
+
+    // ---------------- pair task: per-centre exponent pieces A', B, U' (pre-scaled by EXP_SC) ----------------
+    // Global traffic is staged through shared memory in blocks of 128 centres so that the X rows are read and the
+    // U' rows are written with fully coalesced 16-byte accesses (a thread-per-row 8-byte pattern costs one L2
+    // transaction per double).
+    const int q = task - E;
+    int a, b;
+    if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);
+    const double* Qg = wsr + L.Qab + (size_t)q * 2 * MAXD * MAXD;
+    for (int e = tid; e < DP * DP; e += blockDim.x) { sQa[e] = Qg[e]; sQb[e] = Qg[MAXD * MAXD + e]; }
+    if (tid < DP) {
+        const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
+        pa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
+        pb[tid] = tid < D ? 1.0 / (lb * lb) : 0.0;
+    }
+    __syncthreads();
+    const double lsa = log(sf2[a]), lsb = log(sf2[b]);
+    const double hld = wsr[L.Qh + q];
+    const int lds = ldz | 1;                                    // odd row stride in smem: conflict-light
+    for (int n0 = 0; n0 < np; n0 += 128) {
+        // coalesced load of X[n0 : n0+128, :] (contiguous in global) into sStage[row][d]
+        const int rows = (n - n0) < 128 ? ((n - n0) > 0 ? (n - n0) : 0) : 128;
+        __syncthreads();
+        for (int e = tid; e < rows * D; e += blockDim.x) sStage[(e / D) * lds + (e % D)] = X[(size_t)n0 * D + e];
+        __syncthreads();
+        const int nn = n0 + tid;
         double Apv = NEG_PAD, Bqv = NEG_PAD;
         double u[DP];
 #pragma unroll
@@ -294,7 +358,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
             double ka = lsa, kb = lsb;
 #pragma unroll
             for (int d = 0; d < DP; ++d) {
-                z[d] = d < D ? X[(size_t)nn * D + d] - sm[d] : 0.0;
+                z[d] = d < D ? sStage[tid * lds + d] - sm[d] : 0.0;
                 const double z2 = z[d] * z[d];
                 ka = fma(-0.5 * pa[d], z2, ka);
                 kb = fma(-0.5 * pb[d], z2, kb);
@@ -305,32 +369,47 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS, 3) mm_setup_kernel(MMParams 
                 double va = 0.0, vb = 0.0;                     // (Q z_a)[i], (Q z_b)[i]
 #pragma unroll
                 for (int j = 0; j < DP; ++j) {
-                    va = fma(Qs[i * SLD + j], z[j], va);
-                    vb = fma(Ls[i * SLD + j], z[j], vb);
+                    va = fma(sQa[i * DP + j], z[j], va);
+                    vb = fma(sQb[i * DP + j], z[j], vb);
                 }
                 qa = fma(pa[i] * z[i], va, qa);
                 qb = fma(pb[i] * z[i], vb, qb);
-                u[i] = 2.0 * pb[i] * va;                       // U' = p_b o (2 Q z_a)
+                u[i] = (2.0 * EXP_SC) * pb[i] * va;            // U' = p_b o (2 Q z_a), pre-scaled
             }
             Apv = EXP_SC * (ka + qa - hld);                     // exponents are stored pre-scaled (exp_scaled)
             Bqv = EXP_SC * (kb + qb);
-#pragma unroll
-            for (int i = 0; i < DP; ++i) u[i] *= EXP_SC;
-        }
-        if (BWD) {
-            if (b == 0) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
-            if (q == 0) {
-                for (int d = 0; d < ldz; ++d)
-                    wsr[L.zeta + (size_t)nn * ldz + d] = (nn < n && d < D) ? X[(size_t)nn * D + d] - sm[d] : 0.0;
+            if (BWD && q == 0) {
+                for (int d = 0; d < ldz; ++d) wsr[L.zeta + (size_t)nn * ldz + d] = d < DP ? z[d] : 0.0;
             }
+        } else if (BWD && q == 0 && nn < np) {
+            for (int d = 0; d < ldz; ++d) wsr[L.zeta + (size_t)nn * ldz + d] = 0.0;
         }
-        wsr[L.Ap + (size_t)q * np + nn] = Apv;
-        wsr[L.Bq + (size_t)q * np + nn] = Bqv;
-        double* up = wsr + L.U + ((size_t)q * np + nn) * ldz;
+        if (nn < np) {
+            if (BWD && b == 0) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
+            wsr[L.Ap + (size_t)q * np + nn] = Apv;
+            wsr[L.Bq + (size_t)q * np + nn] = Bqv;
+        }
+        // U' block: registers -> smem [row][ldz] (dense) -> coalesced double2 stores
+        __syncthreads();
 #pragma unroll
-        for (int d = 0; d < DP; ++d) up[d] = u[d];
-        for (int d = DP; d < ldz; ++d) up[d] = 0.0;
+        for (int d = 0; d < DP; ++d) sStage[tid * lds + d] = u[d];
+        for (int d = DP; d < ldz; ++d) sStage[tid * lds + d] = 0.0;
+        __syncthreads();
+        const int rows_out = (np - n0) < 128 ? (np - n0) : 128;
+        double2* dst = reinterpret_cast<double2*>(wsr + L.U + ((size_t)q * np + n0) * ldz);
+        for (int e = tid; e < rows_out * ldz / 2; e += blockDim.x) {
+            const int rr = (2 * e) / ldz, cc = (2 * e) % ldz;   // ldz is even: a double2 never straddles rows
+            dst[e] = make_double2(sStage[rr * lds + cc], sStage[rr * lds + cc + 1]);
+        }
     }
+}
+
+// both stages
+template <int DP, bool BWD>
+static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
+    const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
+    mm_setup1_kernel<DP, BWD><<<dim3((ntask + SETUP_WARPS - 1) / SETUP_WARPS, p.R), 32 * SETUP_WARPS, 0, st>>>(p);
+    mm_setup2_kernel<DP, BWD><<<dim3(ntask, p.R), 128, 0, st>>>(p);
 }
 
 // -------------------------------------------------------------------------------------------------
