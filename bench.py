@@ -213,8 +213,10 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=d)       # > L2 (126 MB)
     gathered = [torch.empty(R, dtype=torch.float64, device=d) for _ in range(world)]
 
+    plan.capture(backward=False)               # the H-step loop as ONE CUDA graph (6H+1 kernel nodes)
+
     def step_resident():
-        plan.forward()
+        plan.replay()
         if world > 1:
             dist.all_gather(gathered, plan.reward)
 

@@ -257,6 +257,26 @@ class RolloutPlan:
         check(lib.pilco_rollout_forward(C.byref(self.ro), stream_ptr()), "rollout_forward")
         return self.traj_m, self.traj_S, self.reward
 
+    # ---- CUDA graph: the whole H-step loop (6H+1 launches forward, ~10H backward) as one graph launch -------
+    def capture(self, backward=False):
+        """Capture forward (and optionally the reverse sweep) into a CUDA graph.  Buffers are static, the C
+        entry points only enqueue work on the current stream, so stream capture records every launch."""
+        self.forward()                       # warm-up: one-time function attributes / table upload happen here
+        if backward:
+            self.backward()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.forward()
+            if backward:
+                self.backward()
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
+        return self.traj_m, self.traj_S, self.reward
+
     def backward(self):
         """pilco_rollout_backward: d reward[r] / d policy parameters (call after forward()).
         Linear: {'W': [R,U,Ds], 'b': [R,U]};  RBF: {'X': [R,bf,Ds], 'Y': [R,bf,U], 'ell': [R,U,Ds]}."""

@@ -47,10 +47,36 @@ class PolicyEvaluator:
         self.d_out = torch.empty((R, self.P + 2), dtype=torch.float64, device=engine.device())
 
     def __call__(self, flats):
-        """flats [R,P] (numpy) -> loss [R], grad [R,P]; non-finite restarts get (BIG, 0)."""
+        """flats [R,P] (numpy) -> loss [R], grad [R,P]; non-finite restarts get (BIG, 0).
+        The first call runs eagerly (warm-up), the second captures the whole evaluation -- parameter unpacking,
+        policy factorisation, H-step forward cascade, reverse sweep, gradient packing -- into one CUDA graph
+        that every later L-BFGS evaluation replays."""
+        self.h_flat.copy_(torch.as_tensor(flats))
+        self.ncalls = getattr(self, "ncalls", 0) + 1
+        if getattr(self, "graph", None) is not None:
+            self.graph.replay()
+        elif self.ncalls == 2 and self.use_graph:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue()
+            self.graph = g
+            g.replay()
+        else:
+            self._enqueue()
+        torch.cuda.current_stream().synchronize()
+        res = self.h_out.numpy()
+        loss, bad, grad = res[:, 0].copy(), res[:, 1] != 0, res[:, 2:].copy()
+        bad |= ~np.isfinite(loss) | ~np.isfinite(grad).all(axis=1)
+        loss[bad] = BIG
+        grad[bad] = 0.0
+        return loss, grad
+
+    use_graph = True
+
+    def _enqueue(self):
         R, P = self.R, self.P
         Ds, U = self.shape
-        self.h_flat.copy_(torch.as_tensor(flats))
         self.d_flat.copy_(self.h_flat, non_blocking=True)
         plan = self.plan
         if self.linear:
@@ -78,13 +104,6 @@ class PolicyEvaluator:
             out[:, 2 + bf * Ds:2 + bf * Ds + bf * U] = -g["Y"].reshape(R, -1)
             out[:, 2 + bf * Ds + bf * U:] = -(g["ell"] * torch.sigmoid(th)).reshape(R, -1)
         self.h_out.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        res = self.h_out.numpy()
-        loss, bad, grad = res[:, 0].copy(), res[:, 1] != 0, res[:, 2:].copy()
-        bad |= ~np.isfinite(loss) | ~np.isfinite(grad).all(axis=1)
-        loss[bad] = BIG
-        grad[bad] = 0.0
-        return loss, grad
 
 
 class LockstepLBFGS:

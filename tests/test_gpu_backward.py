@@ -142,3 +142,35 @@ def test_rbf_policy_optimisation_improves_reward():
     pilco.optimize_policy(maxiter=15, restarts=3)
     r1 = float(pilco.compute_reward())
     assert np.isfinite(r1) and r1 >= r0 - 1e-9
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured H-step loop (forward + reverse sweep) must reproduce the eager results bit for bit, and keep
+    doing so after the policy parameters are overwritten in place."""
+    from pilco_b200 import engine, _lib
+    Ds, U, n, H, bf, R = 3, 1, 40, 5, 8, 3
+    D = Ds + U
+    X, Y, ell, sf2, sn2 = make_gp_problem(n, D, Ds, seed=4)
+    gp = engine.gp_factorize(X, 0.1 * Y, ell, sf2, sn2)
+    rng = np.random.RandomState(0)
+    Xc, Yc, lc = rng.randn(R, bf, Ds), 0.1 * rng.randn(R, bf, U), 1.0 + 0.1 * rng.randn(R, U, Ds)
+    pgp = engine.gp_factorize(Xc, Yc, lc, np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
+    spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=np.array([2.0]), gp=pgp)
+    plan = engine.RolloutPlan(gp, spec, [dict(kind=_lib.REWARD_EXP, coef=1.0, W=np.eye(Ds), t=np.zeros(Ds))],
+                              X[0, :Ds], 0.1 * np.eye(Ds), H, R=R)
+    plan.forward(); g0 = {k: v.clone() for k, v in plan.backward().items()}
+    r0, m0 = plan.reward.clone(), plan.traj_m.clone()
+    plan.capture(backward=True)
+    plan.reward.zero_()
+    plan.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.reward, r0) and torch.equal(plan.traj_m, m0)
+    for k in ("X", "Y", "ell"):
+        assert torch.equal(plan.gbuf[k], g0[k])
+    # new parameters in the same buffers -> refactorise -> replay == eager
+    pgp.Y.mul_(1.5)
+    engine.gp_refactorize(pgp)
+    plan.replay(); torch.cuda.synchronize()
+    r1 = plan.reward.clone()
+    plan.forward(); torch.cuda.synchronize()
+    assert torch.equal(plan.reward, r1) and not torch.equal(r1, r0)
