@@ -40,10 +40,8 @@ __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
     const int row = row0 + g;
     const bool active = row0 < p.gp.n;
 
-    double ua[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)q * np + row) * ldz + 4 * ks + t];
-    const double Apv = wsr[L.Ap + (size_t)q * np + row];
+    double ua[KS], Apv;
+    tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < p.gp.n, lane, ua, Apv);
     const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
     const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
 

@@ -13,9 +13,17 @@
 #include "common.cuh"
 
 #define TILE_CM 512        // columns staged in shared memory per chunk
+// per-pair constants written by setup stage 1: Qa = Q diag(p_a) [MAXD*MAXD], Qb = Q diag(p_b), p_a, p_b,
+// 0.5 log det R, log sf2_a, log sf2_b
+#define PAIR_QA 0
+#define PAIR_QB (MAXD * MAXD)
+#define PAIR_PA (2 * MAXD * MAXD)
+#define PAIR_PB (2 * MAXD * MAXD + MAXD)
+#define PAIR_SC (2 * MAXD * MAXD + 2 * MAXD)
+#define PAIR_BLK (2 * MAXD * MAXD + 2 * MAXD + 8)
 
 struct MMWs {            // workspace layout, offsets in doubles relative to the per-restart base
-    size_t zeta, betap, Ap, Bq, U, Tpart, Wm, Wc, Qab, Qh, per_r;
+    size_t zeta, betap, Bq, Tpart, Wm, Wc, Qab, per_r;
     int np, ldz, P, NB;
 };
 
@@ -25,15 +33,12 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     size_t o = 0;
     L.zeta = o;  o += (size_t)L.np * L.ldz;
     L.betap = o; o += (size_t)E * L.np;
-    L.Ap = o;    o += (size_t)L.P * L.np;
     L.Bq = o;    o += (size_t)L.P * L.np;
-    L.U = o;     o += (size_t)L.P * L.np * L.ldz;
     L.Tpart = o; o += (size_t)L.P * L.NB;
     o = (o + 1) & ~(size_t)1;
     L.Wm = o;    o += (size_t)E * MAXD * MAXD;          // setup stage 1 -> 2: W_a
     L.Wc = o;    o += (size_t)((E + 1) & ~1);           //                      c_a
-    L.Qab = o;   o += (size_t)L.P * 2 * MAXD * MAXD;    //                      Q diag(p_a), Q diag(p_b)
-    L.Qh = o;    o += (size_t)((L.P + 1) & ~1);         //                      0.5 log det R_ab
+    L.Qab = o;   o += (size_t)L.P * PAIR_BLK;           //                      per-pair block (see PAIR_*)
     L.per_r = (o + 1) & ~(size_t)1;
     return L;
 }
@@ -215,13 +220,16 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p)
 #pragma unroll
     for (int i = 0; i < DP; ++i) qsym[i] = 0.5 * (Qs[i * SLD + li] + Qs[li * SLD + i]);
     // stage-2 operands: Qa = Q diag(p_a), Qb = Q diag(p_b) (column `lane`), and 0.5 log det R
-    double* Qo2 = wsr + L.Qab + (size_t)q * 2 * MAXD * MAXD;
+    double* Qo2 = wsr + L.Qab + (size_t)q * PAIR_BLK;
     if (lane < DP) {
 #pragma unroll
-        for (int i = 0; i < DP; ++i) { Qo2[i * DP + lane] = qsym[i] * pa[lane]; Qo2[MAXD * MAXD + i * DP + lane] = qsym[i] * pb[lane]; }
+        for (int i = 0; i < DP; ++i) { Qo2[PAIR_QA + i * DP + lane] = qsym[i] * pa[lane]; Qo2[PAIR_QB + i * DP + lane] = qsym[i] * pb[lane]; }
     }
+    if (lane < MAXD) { Qo2[PAIR_PA + lane] = lane < DP ? pa[lane] : 0.0; Qo2[PAIR_PB + lane] = lane < DP ? pb[lane] : 0.0; }
     if (lane == 0) {
-        wsr[L.Qh + q] = 0.5 * ldet;
+        Qo2[PAIR_SC + 0] = 0.5 * ldet;
+        Qo2[PAIR_SC + 1] = log(sf2[a]);
+        Qo2[PAIR_SC + 2] = log(sf2[b]);
         if (!ok && p.info) atomicOr(&p.info[r], 1);
     }
     if (BWD) {
@@ -247,7 +255,8 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
     const MMWs& L = p.L;
-    const int np = L.np, ldz = L.ldz;
+    const int np = L.np;
+    constexpr int ldz = DP <= 4 ? 4 : (DP <= 12 ? 12 : 20);   // == L.ldz (ldz_of), compile-time so /,% by it are cheap
     const int tid = threadIdx.x;
     const int task = BWD ? blockIdx.x + E : blockIdx.x;
 
@@ -278,7 +287,10 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
         for (int n0 = 0; n0 < np; n0 += 128) {
             const int rows = (n - n0) < 128 ? ((n - n0) > 0 ? (n - n0) : 0) : 128;
             __syncthreads();
-            for (int e = tid; e < rows * D; e += blockDim.x) sStage[(e / D) * lds + (e % D)] = X[(size_t)n0 * D + e];
+            for (int e = tid; e < rows * ldz; e += blockDim.x) {
+                const int rr = e / ldz, cc = e % ldz;
+                if (cc < D) sStage[rr * lds + cc] = X[(size_t)(n0 + rr) * D + cc];
+            }
             __syncthreads();
             const int nn = n0 + tid;
             double z[DP];
@@ -324,83 +336,127 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
         return;
     }
 
-    // ---------------- pair task: per-centre exponent pieces A', B, U' (pre-scaled by EXP_SC) ----------------
-    // Global traffic is staged through shared memory in blocks of 128 centres so that the X rows are read and the
-    // U' rows are written with fully coalesced 16-byte accesses (a thread-per-row 8-byte pattern costs one L2
-    // transaction per double).
+    // ---------------- pair task: column-side exponent piece B_ab[m] = k_b[m] + z_b' Q z_b (pre-scaled) --------
+    // (Q diag p_b) zeta_m for 8 centres at a time as a small fp64-DMMA GEMM Z[8 x DP] . Qb^T; the row-side
+    // pieces A'_ab[n], U'_ab[n] are NOT materialised: every tile CTA derives them for its own 64 rows
+    // (tile_row_operands below).
     const int q = task - E;
     int a, b;
     if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);
-    const double* Qg = wsr + L.Qab + (size_t)q * 2 * MAXD * MAXD;
-    for (int e = tid; e < DP * DP; e += blockDim.x) { sQa[e] = Qg[e]; sQb[e] = Qg[MAXD * MAXD + e]; }
-    if (tid < DP) {
-        const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
-        pa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
-        pb[tid] = tid < D ? 1.0 / (lb * lb) : 0.0;
-    }
+    constexpr int KS = DP / 4, NT = (DP + 7) / 8;
+    const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const double* blk = wsr + L.Qab + (size_t)q * PAIR_BLK;
+    for (int e = tid; e < DP * DP; e += blockDim.x) sQb[e] = blk[PAIR_QB + e];
+    if (tid < MAXD) pb[tid] = blk[PAIR_PB + tid];
     __syncthreads();
-    const double lsa = log(sf2[a]), lsb = log(sf2[b]);
-    const double hld = wsr[L.Qh + q];
-    const int lds = ldz | 1;                                    // odd row stride in smem: conflict-light
+    double bqb[KS][NT];                                         // B fragments: B[k][n] = Qb[n][k]
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int i = 8 * nt + g;
+            bqb[ks][nt] = i < DP ? sQb[i * DP + 4 * ks + t] : 0.0;
+        }
+    const double lsb = blk[PAIR_SC + 2];
     for (int n0 = 0; n0 < np; n0 += 128) {
-        // coalesced load of X[n0 : n0+128, :] (contiguous in global) into sStage[row][d]
-        const int rows = (n - n0) < 128 ? ((n - n0) > 0 ? (n - n0) : 0) : 128;
+        // stage zeta[n0 : n0+128, 0:ldz] = X - m (zero outside [n, D)) in shared memory, coalesced
         __syncthreads();
-        for (int e = tid; e < rows * D; e += blockDim.x) sStage[(e / D) * lds + (e % D)] = X[(size_t)n0 * D + e];
-        __syncthreads();
-        const int nn = n0 + tid;
-        double Apv = NEG_PAD, Bqv = NEG_PAD;
-        double u[DP];
-#pragma unroll
-        for (int d = 0; d < DP; ++d) u[d] = 0.0;
-        if (nn < n) {
-            double z[DP];
-            double ka = lsa, kb = lsb;
-#pragma unroll
-            for (int d = 0; d < DP; ++d) {
-                z[d] = d < D ? sStage[tid * lds + d] - sm[d] : 0.0;
-                const double z2 = z[d] * z[d];
-                ka = fma(-0.5 * pa[d], z2, ka);
-                kb = fma(-0.5 * pb[d], z2, kb);
-            }
-            double qa = 0.0, qb = 0.0;
-#pragma unroll
-            for (int i = 0; i < DP; ++i) {
-                double va = 0.0, vb = 0.0;                     // (Q z_a)[i], (Q z_b)[i]
-#pragma unroll
-                for (int j = 0; j < DP; ++j) {
-                    va = fma(sQa[i * DP + j], z[j], va);
-                    vb = fma(sQb[i * DP + j], z[j], vb);
-                }
-                qa = fma(pa[i] * z[i], va, qa);
-                qb = fma(pb[i] * z[i], vb, qb);
-                u[i] = (2.0 * EXP_SC) * pb[i] * va;            // U' = p_b o (2 Q z_a), pre-scaled
-            }
-            Apv = EXP_SC * (ka + qa - hld);                     // exponents are stored pre-scaled (exp_scaled)
-            Bqv = EXP_SC * (kb + qb);
-            if (BWD && q == 0) {
-                for (int d = 0; d < ldz; ++d) wsr[L.zeta + (size_t)nn * ldz + d] = d < DP ? z[d] : 0.0;
-            }
-        } else if (BWD && q == 0 && nn < np) {
-            for (int d = 0; d < ldz; ++d) wsr[L.zeta + (size_t)nn * ldz + d] = 0.0;
+        for (int e = tid; e < 128 * ldz; e += blockDim.x) {
+            const int rr = e / ldz, cc = e % ldz;
+            sStage[e] = (n0 + rr < n && cc < D) ? X[(size_t)(n0 + rr) * D + cc] - sm[cc] : 0.0;
         }
-        if (nn < np) {
-            if (BWD && b == 0) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
-            wsr[L.Ap + (size_t)q * np + nn] = Apv;
-            wsr[L.Bq + (size_t)q * np + nn] = Bqv;
-        }
-        // U' block: registers -> smem [row][ldz] (dense) -> coalesced double2 stores
         __syncthreads();
+        if (BWD && q == 0) {                                    // backward mode: this task also publishes zeta
+            double2* dz = reinterpret_cast<double2*>(wsr + L.zeta + (size_t)n0 * ldz);
+            const int rows_out = (np - n0) < 128 ? (np - n0) : 128;
+            for (int e = tid; e < rows_out * ldz / 2; e += blockDim.x) dz[e] = make_double2(sStage[2 * e], sStage[2 * e + 1]);
+        }
+        if (BWD && b == 0) {
+            const int nn = n0 + tid;
+            if (nn < np) wsr[L.betap + (size_t)a * np + nn] = nn < n ? beta[(size_t)a * n + nn] : 0.0;
+        }
+        for (int grp = warp; grp < 16; grp += 4) {
+            const int row = n0 + 8 * grp + g;
+            if (n0 + 8 * grp >= np) break;                      // warp-uniform
+            const double* zr = sStage + (size_t)(8 * grp + g) * ldz;
+            double z[KS], vb[NT][2];
+            double kbp = 0.0;
 #pragma unroll
-        for (int d = 0; d < DP; ++d) sStage[tid * lds + d] = u[d];
-        for (int d = DP; d < ldz; ++d) sStage[tid * lds + d] = 0.0;
-        __syncthreads();
-        const int rows_out = (np - n0) < 128 ? (np - n0) : 128;
-        double2* dst = reinterpret_cast<double2*>(wsr + L.U + ((size_t)q * np + n0) * ldz);
-        for (int e = tid; e < rows_out * ldz / 2; e += blockDim.x) {
-            const int rr = (2 * e) / ldz, cc = (2 * e) % ldz;   // ldz is even: a double2 never straddles rows
-            dst[e] = make_double2(sStage[rr * lds + cc], sStage[rr * lds + cc + 1]);
+            for (int ks = 0; ks < KS; ++ks) {
+                z[ks] = zr[4 * ks + t];
+                kbp = fma(pb[4 * ks + t] * z[ks], z[ks], kbp);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { vb[nt][0] = vb[nt][1] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(vb[nt][0], vb[nt][1], z[ks], bqb[ks][nt]);
+            double qbp = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int i0 = 8 * nt + 2 * t;                  // this lane's two columns of the C fragment
+                if (i0 < DP) qbp = fma(pb[i0] * zr[i0], vb[nt][0], fma(pb[i0 + 1] * zr[i0 + 1], vb[nt][1], qbp));
+            }
+            kbp += __shfl_xor_sync(0xffffffffu, kbp, 1); kbp += __shfl_xor_sync(0xffffffffu, kbp, 2);
+            qbp += __shfl_xor_sync(0xffffffffu, qbp, 1); qbp += __shfl_xor_sync(0xffffffffu, qbp, 2);
+            if (t == 0) wsr[L.Bq + (size_t)q * np + row] = row < n ? EXP_SC * (lsb - 0.5 * kbp + qbp) : NEG_PAD;
         }
+    }
+}
+
+// Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
+// U' = 2 EXP_SC p_b o (Qa zeta_row), and the scalar A'[row] = EXP_SC (log sf2_a - 0.5 sum p_a zeta^2 + z_a'Q z_a
+// - 0.5 log det R).  zeta rows are read from the workspace (L2 resident); 2*ceil(DP/8)*KS DMMA + 2 KS shuffles.
+template <int KS>
+__device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk, const double* __restrict__ zeta,
+                                                  int ldz, int row, bool live, int lane,
+                                                  double (&ua)[KS], double& Apv) {
+    constexpr int DP = 4 * KS, NT = (DP + 7) / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const double* zr = zeta + (size_t)row * ldz;
+    const double* pa = blk + PAIR_PA;
+    const double* pb = blk + PAIR_PB;
+    double z[KS], va[NT][2];
+    double kap = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        z[ks] = zr[4 * ks + t];
+        kap = fma(pa[4 * ks + t] * z[ks], z[ks], kap);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { va[nt][0] = va[nt][1] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int i = 8 * nt + g;
+            const double bq = i < DP ? blk[PAIR_QA + i * DP + 4 * ks + t] : 0.0;
+            dmma884(va[nt][0], va[nt][1], z[ks], bq);
+        }
+    double qap = 0.0;
+    double uc[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int i0 = 8 * nt + 2 * t;
+        uc[nt][0] = uc[nt][1] = 0.0;
+        if (i0 < DP) {
+            qap = fma(pa[i0] * zr[i0], va[nt][0], fma(pa[i0 + 1] * zr[i0 + 1], va[nt][1], qap));
+            uc[nt][0] = (2.0 * EXP_SC) * pb[i0] * va[nt][0];
+            uc[nt][1] = (2.0 * EXP_SC) * pb[i0 + 1] * va[nt][1];
+        }
+    }
+    kap += __shfl_xor_sync(0xffffffffu, kap, 1); kap += __shfl_xor_sync(0xffffffffu, kap, 2);
+    qap += __shfl_xor_sync(0xffffffffu, qap, 1); qap += __shfl_xor_sync(0xffffffffu, qap, 2);
+    Apv = live ? EXP_SC * (blk[PAIR_SC + 1] - 0.5 * kap + qap - blk[PAIR_SC + 0]) : NEG_PAD;
+    // C-fragment layout (row g, cols 8nt+2t,+1) -> A-fragment layout (row g, col 4ks+t)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        const int nt = ks >> 1;                                 // col 4ks+t lies in n-tile ks/2 ...
+        const int src = (lane & ~3) | (((ks & 1) << 1) | (t >> 1));   // ... held by quad lane (4(ks&1)+t)/2
+        const double x0 = __shfl_sync(0xffffffffu, uc[nt][0], src);
+        const double x1 = __shfl_sync(0xffffffffu, uc[nt][1], src);
+        ua[ks] = (t & 1) ? x1 : x0;
     }
 }
 
@@ -453,10 +509,8 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     exp_table_init(tab);
-    double ua[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) ua[ks] = wsr[L.U + ((size_t)q * np + row) * ldz + 4 * ks + t];
-    const double Apv = wsr[L.Ap + (size_t)q * np + row];
+    double ua[KS], Apv;
+    tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < n, lane, ua, Apv);
     const double ba = wsr[L.betap + (size_t)a * np + row];
     const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
     __syncthreads();
