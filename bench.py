@@ -207,39 +207,54 @@ def run_ours(args):
     rew = [dict(kind=_lib.REWARD_EXP, coef=1.0, W=wl["W"], t=wl["t"])]
 
     # ---- device-resident arm: policy parameters already in HBM, rollout only --------------------------
-    pgp = engine.gp_factorize(Xc, Yc, lc, ones, noise, need_iK=False, mode=1)
-    spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pgp)
-    plan = engine.RolloutPlan(gp, spec, rew, wl["m0"], wl["S0"], H, R=R)
+    # The H-step loop of all R restarts is ONE CUDA graph: nsplit sub-batches on parallel streams (their
+    # latency-bound per-step kernels overlap each other's tile kernels), 6H+1 kernel nodes per sub-batch.
+    nsplit = max(1, min(args.nsplit, R))
+    pgps = {}
+
+    def make_plan(lo, hi):
+        pg = engine.gp_factorize(Xc[lo:hi], Yc[lo:hi], lc[lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
+        pgps[(lo, hi)] = pg
+        sp = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
+        return engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo)
+
+    split = engine.SplitRollout(make_plan, R, nsplit=nsplit)
+    plan = split.plans[0]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=d)       # > L2 (126 MB)
     gathered = [torch.empty(R, dtype=torch.float64, device=d) for _ in range(world)]
 
-    plan.capture(backward=False)               # the H-step loop as ONE CUDA graph (6H+1 kernel nodes)
-
     def step_resident():
-        plan.replay()
+        rw = split.replay()
         if world > 1:
-            dist.all_gather(gathered, plan.reward)
+            dist.all_gather(gathered, rw)
 
     # ---- end-to-end arm: host buffers in, host result out -----------------------------------------
     # What one optimiser evaluation does through the public engine objects: pinned host policy parameters ->
     # device, policy factorisation (beta = (K+sn2 I)^-1 Y, pilco_gp_factorize), H-step rollout, rewards -> host.
-    # Device work is one captured CUDA graph (refactorise + cascade) replayed per step.
+    # Device work is one captured CUDA graph (refactorise + cascade, same sub-batch split) replayed per step.
     hX = torch.as_tensor(Xc).pin_memory(); hY = torch.as_tensor(Yc).pin_memory(); hl = torch.as_tensor(lc).pin_memory()
     h_out = torch.empty(R, dtype=torch.float64).pin_memory()
     h2d = (hX.numel() + hY.numel() + hl.numel()) * 8
     d2h = R * 8
-    pgp2 = engine.gp_factorize(Xc, Yc, lc, ones, noise, need_iK=False, mode=1)
-    plan2 = engine.RolloutPlan(gp, dict(spec, gp=pgp2), rew, wl["m0"], wl["S0"], H, R=R)
-    engine.gp_refactorize(pgp2); plan2.forward(); torch.cuda.synchronize()
-    g2 = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g2):
-        engine.gp_refactorize(pgp2)
-        plan2.forward()
+    pg2 = {}
+
+    def make_plan2(lo, hi):
+        pg = engine.gp_factorize(Xc[lo:hi], Yc[lo:hi], lc[lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
+        pg2[(lo, hi)] = pg
+        sp = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
+        pl = engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo)
+        fwd = pl.forward
+        pl.forward = lambda: (engine.gp_refactorize(pg), fwd())[1]      # refactorise inside the captured graph
+        return pl
+
+    split2 = engine.SplitRollout(make_plan2, R, nsplit=nsplit)
 
     def step_e2e():
-        pgp2.X.copy_(hX, non_blocking=True); pgp2.Y.copy_(hY, non_blocking=True); pgp2.ell.copy_(hl, non_blocking=True)
-        g2.replay()
-        h_out.copy_(plan2.reward, non_blocking=True)
+        for (lo, hi), pg in pg2.items():
+            pg.X.copy_(hX[lo:hi], non_blocking=True); pg.Y.copy_(hY[lo:hi], non_blocking=True)
+            pg.ell.copy_(hl[lo:hi], non_blocking=True)
+        rw = split2.replay()
+        h_out.copy_(rw, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def timed(fn, K, W):
@@ -266,12 +281,19 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
         return float(t.item()) / K                             # ms per step
 
+    # ---- forward + reverse sweep (policy gradient), device resident: extra line, not the headline -----------
+    split3 = engine.SplitRollout(make_plan, R, nsplit=nsplit, backward=True) if args.with_backward else None
+
+    def step_fwd_bwd():
+        split3.replay()
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_res = timed(step_resident, args.steps, args.warmup)
-    ok = int(plan.info.max().item()) == 0 and bool(torch.isfinite(plan.reward).all().item())
+    ok = int(split.info.max().item()) == 0 and bool(torch.isfinite(split.reward).all().item())
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    ms_fb = timed(step_fwd_bwd, max(3, args.steps // 2), 2) if split3 is not None else None
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -287,7 +309,6 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel (dynamics mm_tile) -------------------------------------------
     ms3 = (C.c_float * 3)()
-    m_in = plan.ws[:R * D].clone()      # any finite inputs of the right shape: use the last joint Gaussian
     from pilco_b200.engine import ptr, stream_ptr
     g = gp.struct()
     E = Ds
@@ -339,15 +360,18 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
     cpu_v, cores, sample = cpu_reference_steps_per_s(wl, reps=2, h_sample=4)
-    launches_per_step = (H * 6 + 1) + 1                             # ro_state + policy(setup,tile,ro_policy) + dyn(setup,tile); +memset
+    launches_per_step = nsplit * ((H * 8 + 1) + 1)                  # per sub-batch: ro_state + policy(setup1,setup2,tile,ro_policy) + dyn(setup1,setup2,tile); +memset
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "metric config: N=300 E=Ds=10 U=2 D=12 H=40, RBF policy bf=50, R=%d restarts/GPU, forward rollout" % R,
-                   "restarts_per_gpu": R, "l2": "flushed between timed iterations (256 MiB write)", "finite": ok},
+                   "restarts_per_gpu": R, "graph": "one CUDA graph per rollout batch, %d sub-batches on parallel streams" % nsplit, "l2": "flushed between timed iterations (256 MiB write)", "finite": ok},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "what": "pinned host policy parameters -> device, policy factorisation, H-step rollout, rewards -> host"},
+        "fwd_bwd": ({"value": total_steps / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb,
+                     "what": "forward cascade + hand-derived reverse sweep (policy gradient), device resident"}
+                    if ms_fb is not None else None),
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -365,6 +389,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--restarts", type=int, default=32, help="policy restarts per GPU")
+    ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward extra line")
+    ap.add_argument("--nsplit", type=int, default=4, help="sub-batches on parallel streams inside the captured graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -305,3 +305,53 @@ class RolloutPlan:
             self.grad = g
         check(lib.pilco_rollout_backward(C.byref(self.ro), C.byref(self.grad), stream_ptr()), "rollout_backward")
         return self.gbuf
+
+
+class SplitRollout:
+    """R independent rollouts as ``nsplit`` sub-batches on parallel streams inside ONE captured CUDA graph.
+
+    Within a rollout the per-step kernels are strictly sequential, and several of them (state/policy glue,
+    the D x D Cholesky stage) are latency-bound on a handful of SMs; running sub-batches on separate streams lets
+    those overlap another sub-batch's tile kernel.  ``make_plan(lo, hi)`` must build the RolloutPlan of restarts
+    [lo, hi)."""
+
+    def __init__(self, make_plan, R, nsplit=4, backward=False):
+        nsplit = max(1, min(int(nsplit), int(R)))
+        bounds = [round(k * R / nsplit) for k in range(nsplit + 1)]
+        self.slices = [(bounds[k], bounds[k + 1]) for k in range(nsplit) if bounds[k + 1] > bounds[k]]
+        self.plans = [make_plan(lo, hi) for lo, hi in self.slices]
+        self.backward = backward
+        self.R = R
+        for p in self.plans:                       # eager warm-up (one-time attributes, allocations)
+            p.forward()
+            if backward:
+                p.backward()
+        torch.cuda.synchronize()
+        self.side = [torch.cuda.Stream() for _ in self.plans[1:]]
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            cur = torch.cuda.current_stream()
+            for st in self.side:
+                st.wait_stream(cur)
+            self._run(self.plans[0])
+            for st, p in zip(self.side, self.plans[1:]):
+                with torch.cuda.stream(st):
+                    self._run(p)
+            for st in self.side:
+                cur.wait_stream(st)
+        self.reward = torch.empty(R, dtype=F64, device=device())
+
+    def _run(self, p):
+        p.forward()
+        if self.backward:
+            p.backward()
+
+    def replay(self):
+        self.graph.replay()
+        for (lo, hi), p in zip(self.slices, self.plans):
+            self.reward[lo:hi].copy_(p.reward, non_blocking=True)
+        return self.reward
+
+    @property
+    def info(self):
+        return torch.cat([p.info for p in self.plans])
