@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 CFG = dict(N=300, Ds=10, U=2, H=40, bf=50)
 METRIC = "moment-match rollout steps/sec (N=300, E=10, H=40, fp64)"
 UNIT = "rollout-steps/s"
-EXP_FLOP_EQ = 22.0          # fp64 flop-equivalents of one exp: 11 fp64 instructions (10 FMA-class + 1 add), FMA = 2
+EXP_FLOP_EQ = 16.0          # fp64 flop-equivalents of one exp: the kernel's 8 fp64-pipe instructions, counted as 2 each
 
 
 def make_workload(seed=0, R=32):
@@ -335,22 +335,33 @@ def run_ours(args):
     _lib.check(lib.pilco_microbench_fp64(1, iters, blocks, ptr(sink), C.byref(msf), stream_ptr()))
     dmma_tf = 2 * blocks * 8 * iters * 16.0 * 256 / (msf.value * 1e-3) / 1e12
     P = E * (E + 1) // 2
-    elems = float(P) * N * N * R                                   # algorithmic pair-elements per launch
-    dot_flops = 2.0 * D * elems                                    # Q-contraction (DMMA)
-    other_flops = (4.0 + EXP_FLOP_EQ) * elems + 2.0 * E * N * N * R    # exponent assembly, exp, beta^T L beta, trace
+    # algorithmic pair-elements per launch: symmetric (a == a) pairs need only half of their n x n elements
+    elems = (float(P) - 0.5 * E) * N * N * R
+    dot_flops = 2.0 * D * elems                                    # Q-contraction U'.zeta (DMMA)
+    other_flops = (4.0 + EXP_FLOP_EQ) * elems + 2.0 * (0.5 * E * N * N * R)   # exponent add, exp, beta-weighted sum; trace term
     flops = dot_flops + other_flops
     achieved = flops / (tile_ms * 1e-3) / 1e12
-    peak_eff = flops / (dot_flops / dmma_tf + other_flops / dfma_tf)   # time-weighted fp64 peak for this op mix
-    alg_bytes = 8.0 * (E * N * N + R * (N * D + 2 * E * N + P * N * (D + 2)))   # iK once + per-restart operands
+    peak_eff = flops / (dot_flops / dmma_tf + other_flops / dfma_tf)   # time-weighted fp64 peak for this kernel's op mix
+    # compulsory bytes per launch: iK once (shared, L2 resident) + per restart zeta, beta, B_q and the per-pair blocks
+    alg_bytes = 8.0 * (E * N * N + R * (N * D + E * N + P * N + P * 552))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None                       # dram bytes per launch of the same kernel/config from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tile_traffic.json")))
+        if R == 32:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "bound": "tensor", "kernel": "mm_tile_kernel<3> (dynamics GP, fp64 DMMA + DFMA/exp)",
-        "achieved": achieved, "peak": peak_eff, "unit": "TFLOP/s", "frac": achieved / peak_eff, "traffic": None,
+        "bound": "tensor", "kernel": "mm_tile_kernel<3,3> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)",
+        "achieved": achieved, "peak": peak_eff, "unit": "TFLOP/s", "frac": achieved / peak_eff, "traffic": traffic,
+        "traffic_source": "profiles/r01_mm_tile_ncu_full_final.txt (ncu --set full, same kernel and config)" if traffic else None,
+        "algorithmic_bytes": alg_bytes,
         "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), "
                        "time-weighted for this kernel's op mix; MEASURED_PEAKS.json holds no fp64 figure" % (dfma_tf, dmma_tf),
         "q_contraction_tflops": dot_flops / (tile_ms * 1e-3) / 1e12,
