@@ -187,7 +187,7 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 
 // table T[j] = 2^(j/EXP_TAB), correctly rounded on the host, uploaded once (exp_table_upload)
 // (one copy per translation unit: the library is built without relocatable device code)
-static __device__ double g_exp_tab[EXP_TAB];
+static __device__ __align__(16) double g_exp_tab[EXP_TAB];
 static int exp_table_upload() {
     static bool done = false;
     if (done) return PILCO_OK;

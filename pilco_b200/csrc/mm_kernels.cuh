@@ -508,26 +508,37 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
     const int cfirst = sympair ? rb * 64 : 0;
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    exp_table_init(tab);
+    __syncthreads();                                    // barrier initialised (nothing else precedes: cheap)
+
+    // stage one column chunk (zeta rows, B_q, beta_b) and, with the first chunk, the exp table
+    auto issue_chunk = [&](int c0, bool with_table) {
+        const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
+        const int cm = (np - c0) < CM ? (np - c0) : CM;
+        const int ncopy = cm - lo;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)(ncopy * ldz * 8 + ncopy * 16 + (with_table ? EXP_TAB * 8 : 0)));
+        tma_bulk_g2s(sZ + (size_t)lo * ldz, wsr + L.zeta + (size_t)(c0 + lo) * ldz, (unsigned)(ncopy * ldz * 8), bar);
+        tma_bulk_g2s(sBq + lo, wsr + L.Bq + (size_t)q * np + c0 + lo, (unsigned)(ncopy * 8), bar);
+        tma_bulk_g2s(sBe + lo, wsr + L.betap + (size_t)b * np + c0 + lo, (unsigned)(ncopy * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
+    };
+    const int cbeg = (cfirst / CM) * CM;
+    if (tid == 0 && cbeg < ncol8) issue_chunk(cbeg, true);
+    // row operands are computed while the copies are in flight
     double ua[KS], Apv;
     tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < n, lane, ua, Apv);
     const double ba = wsr[L.betap + (size_t)a * np + row];
     const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
-    __syncthreads();
 
     double acc2 = 0.0, accd = 0.0, tr2 = 0.0, trd = 0.0;   // strictly-upper / diagonal-tile accumulators
     unsigned phase = 0;
-    for (int c0 = (cfirst / CM) * CM; c0 < ncol8; c0 += CM) {
+    for (int c0 = cbeg; c0 < ncol8; c0 += CM) {
         const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
         const int cm = (np - c0) < CM ? (np - c0) : CM;
         const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;        // chunk-local end of valid columns
-        const int ncopy = cm - lo;
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)(ncopy * ldz * 8 + ncopy * 16));
-            tma_bulk_g2s(sZ + (size_t)lo * ldz, wsr + L.zeta + (size_t)(c0 + lo) * ldz, (unsigned)(ncopy * ldz * 8), bar);
-            tma_bulk_g2s(sBq + lo, wsr + L.Bq + (size_t)q * np + c0 + lo, (unsigned)(ncopy * 8), bar);
-            tma_bulk_g2s(sBe + lo, wsr + L.betap + (size_t)b * np + c0 + lo, (unsigned)(ncopy * 8), bar);
+        if (c0 != cbeg) {
+            __syncthreads();                                           // all warps done with the previous chunk
+            if (tid == 0) issue_chunk(c0, false);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
@@ -595,7 +606,6 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
                 }
             }
         }
-        __syncthreads();
     }
     // row sums -> beta_a-weighted total; symmetric pairs: diagonal tile once, strictly-upper tiles twice
     double acc = sympair ? accd + 2.0 * acc2 : acc2;
