@@ -17,8 +17,10 @@ static inline __host__ __device__ size_t mm_btile_smem_bytes(int np, int ldz) {
     return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
 }
 
-template <int KS>
-__global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
+// DIAG = true : grid (NB, E, R), the pairs (a,a) of a GP with trace term (iK-weighted sums as well);
+// DIAG = false: grid (NB, E*E, R), every other ordered pair (CTAs of (a,a) pairs that DIAG handles exit at once).
+template <int KS, bool DIAG>
+__global__ void __launch_bounds__(256, DIAG ? 2 : 3) mm_btile_kernel(MMBwdParams bp) {
     constexpr int DP = 4 * KS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMParams& p = bp.f;
@@ -31,41 +33,50 @@ __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
     double* tab = sBe + CM;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
 
-    const int r = blockIdx.z, q = blockIdx.y, rb = blockIdx.x;
+    const int r = blockIdx.z, rb = blockIdx.x;
+    const bool has_trace = (p.gp.mode == 0) && (p.gp.iK != nullptr);
+    const int q = DIAG ? blockIdx.y * E + blockIdx.y : blockIdx.y;
     const int a = q / E, b = q % E;
+    if (!DIAG && a == b && has_trace) return;           // handled by the DIAG instantiation
     double* wsr = p.ws + (size_t)r * bp.B.per_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int row0 = rb * 64 + warp * 8;
     const int row = row0 + g;
     const bool active = row0 < p.gp.n;
+    const int ncol8 = (p.gp.n + 7) & ~7;
 
-    double ua[KS], Apv;
-    tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < p.gp.n, lane, ua, Apv);
-    const bool diag = (a == b) && (p.gp.mode == 0) && (p.gp.iK != nullptr);
-    const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
-
-    exp_table_init(tab);
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
-
-    double accL[DP + 1], accK[DP + 1];
-#pragma unroll
-    for (int i = 0; i <= DP; ++i) { accL[i] = 0.0; accK[i] = 0.0; }
-    unsigned phase = 0;
-    for (int c0 = 0; c0 < np; c0 += CM) {
+    auto issue_chunk = [&](int c0, bool with_table) {
         const int cm = (np - c0) < CM ? (np - c0) : CM;
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16));
-            tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
-            tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
-            tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB * 8 : 0)));
+        tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
+        tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
+        tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
+    };
+    if (tid == 0) issue_chunk(0, true);
+    double ua[KS], Apv;
+    tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < p.gp.n, lane, ua, Apv);
+    const double* ikrow = DIAG ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+
+    double accL[DP + 1], accK[DIAG ? DP + 1 : 1];
+#pragma unroll
+    for (int i = 0; i <= DP; ++i) { accL[i] = 0.0; if (DIAG) accK[i] = 0.0; }
+    unsigned phase = 0;
+    for (int c0 = 0; c0 < ncol8; c0 += CM) {
+        const int cm = (np - c0) < CM ? (np - c0) : CM;
+        const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;
+        if (c0 != 0) {
+            __syncthreads();
+            if (tid == 0) issue_chunk(c0, false);
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         if (active) {
-            for (int col = 0; col < cm; col += 8) {
+            for (int col = 0; col < cend; col += 8) {
                 const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
                 double e0 = Apv + bq.x, e1 = Apv + bq.y;
 #pragma unroll
@@ -76,6 +87,12 @@ __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
                 const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
                 const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                 const double w0 = bb.x * l0, w1 = bb.y * l1;
+                double v0 = 0.0, v1 = 0.0;
+                if (DIAG) {
+                    const double2 ik = *reinterpret_cast<const double2*>(ikrow + c0 + col + 2 * t);
+                    v0 = ik.x * l0; v1 = ik.y * l1;
+                    accK[DP] += v0 + v1;
+                }
                 const double* z0 = sZ + (size_t)(col + 2 * t) * ldz;
                 const double* z1 = z0 + ldz;
                 accL[DP] += w0 + w1;
@@ -85,37 +102,31 @@ __global__ void __launch_bounds__(256, 2) mm_btile_kernel(MMBwdParams bp) {
                     const double2 zb = *reinterpret_cast<const double2*>(z1 + d);
                     accL[d] = fma(w0, za.x, fma(w1, zb.x, accL[d]));
                     accL[d + 1] = fma(w0, za.y, fma(w1, zb.y, accL[d + 1]));
-                }
-                if (diag) {
-                    const double2 ik = *reinterpret_cast<const double2*>(ikrow + c0 + col + 2 * t);
-                    const double v0 = ik.x * l0, v1 = ik.y * l1;
-                    accK[DP] += v0 + v1;
-#pragma unroll
-                    for (int d = 0; d < DP; d += 2) {
-                        const double2 za = *reinterpret_cast<const double2*>(z0 + d);
-                        const double2 zb = *reinterpret_cast<const double2*>(z1 + d);
+                    if (DIAG) {
                         accK[d] = fma(v0, za.x, fma(v1, zb.x, accK[d]));
                         accK[d + 1] = fma(v0, za.y, fma(v1, zb.y, accK[d + 1]));
                     }
                 }
             }
         }
-        __syncthreads();
     }
     // quad reduction (4 lanes share a row), then the quad writes the row's outputs
+    // layout: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK  (hK/HVK only for DIAG pairs)
     double* out = wsr + bp.B.rowout + ((size_t)q * np + row) * bp.B.ldr;
 #pragma unroll
     for (int i = 0; i <= DP; ++i) {
         double v = accL[i];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
-        double k = accK[i];
-        k += __shfl_xor_sync(0xffffffffu, k, 1);
-        k += __shfl_xor_sync(0xffffffffu, k, 2);
-        // layout: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK
         const int slotL = (i == DP) ? 0 : 1 + i;
-        const int slotK = (i == DP) ? DP + 1 : DP + 2 + i;
-        if ((i & 3) == t) { out[slotL] = active ? v : 0.0; out[slotK] = active ? k : 0.0; }
+        if ((i & 3) == t) out[slotL] = active ? v : 0.0;
+        if (DIAG) {
+            double k = accK[i];
+            k += __shfl_xor_sync(0xffffffffu, k, 1);
+            k += __shfl_xor_sync(0xffffffffu, k, 2);
+            const int slotK = (i == DP) ? DP + 1 : DP + 2 + i;
+            if ((i & 3) == t) out[slotK] = active ? k : 0.0;
+        }
     }
 }
 
@@ -448,12 +459,15 @@ static int launch_btile(const MMBwdParams& bp, cudaStream_t st) {
     { int rc0 = exp_table_upload(); if (rc0) return rc0; }
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(mm_btile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)mm_btile_smem_bytes(TILE_CM, 20)) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        const int big = (int)mm_btile_smem_bytes(TILE_CM, 20);
+        if (cudaFuncSetAttribute(mm_btile_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(mm_btile_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }
-    dim3 grid(bp.B.F.NB, bp.B.P2, bp.f.R);
-    mm_btile_kernel<KS><<<grid, 256, smem, st>>>(bp);
+    const int E = bp.f.gp.E;
+    mm_btile_kernel<KS, false><<<dim3(bp.B.F.NB, bp.B.P2, bp.f.R), 256, smem, st>>>(bp);
+    if (bp.f.gp.mode == 0 && bp.f.gp.iK != nullptr)
+        mm_btile_kernel<KS, true><<<dim3(bp.B.F.NB, E, bp.f.R), 256, smem, st>>>(bp);
     return PILCO_OK;
 }
 

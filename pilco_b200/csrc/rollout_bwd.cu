@@ -158,39 +158,45 @@ __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
 __global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int U, const double* X, const double* ell,
                                                              const double* beta, const double* gy,
                                                              double* gX, double* gY, double* gell) {
+    // one CTA per restart, thread n owns centre n: K[n][m] is evaluated once per (n, m, a)
     const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const double* Xr = X + (size_t)r * bf * Ds;
     const double* lr = ell + (size_t)r * U * Ds;
     const double* br = beta + (size_t)r * U * bf;
     const double* gr = gy + (size_t)r * U * bf;
+    __shared__ double sgl[MAXD * 4], sglo[MAXD];
     for (int e = tid; e < bf * U; e += nt) { const int n = e / U, a = e % U; gY[(size_t)r * bf * U + e] = gr[a * bf + n]; }
-    for (int e = tid; e < bf * Ds; e += nt) {
-        const int n = e / Ds, d = e % Ds;
-        double acc = 0.0;
-        for (int a = 0; a < U; ++a) {
-            const double il2 = 1.0 / (lr[a * Ds + d] * lr[a * Ds + d]);
+    for (int a = 0; a < U; ++a) {
+        double il2[MAXD], accl[MAXD];
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) { il2[d] = d < Ds ? 1.0 / (lr[a * Ds + d] * lr[a * Ds + d]) : 0.0; accl[d] = 0.0; }
+        for (int n = tid; n < bf; n += nt) {
+            double xn[MAXD], accx[MAXD];
+#pragma unroll
+            for (int d = 0; d < MAXD; ++d) { xn[d] = d < Ds ? Xr[n * Ds + d] : 0.0; accx[d] = 0.0; }
+            const double gyn = gr[a * bf + n], bn = br[a * bf + n];
             for (int m = 0; m < bf; ++m) {
-                double d2 = 0.0;
-                for (int k = 0; k < Ds; ++k) { const double tt = (Xr[n * Ds + k] - Xr[m * Ds + k]) / lr[a * Ds + k]; d2 = fma(tt, tt, d2); }
+                double diff[MAXD], d2 = 0.0;
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) {
+                    diff[d] = d < Ds ? xn[d] - Xr[m * Ds + d] : 0.0;
+                    d2 = fma(diff[d] * diff[d], il2[d], d2);
+                }
                 const double K = exp(-0.5 * d2);
-                const double P = -(gr[a * bf + n] * br[a * bf + m] + gr[a * bf + m] * br[a * bf + n]) * K;
-                acc = fma(-P * il2, Xr[n * Ds + d] - Xr[m * Ds + d], acc);
+                const double gK = -gyn * br[a * bf + m] * K;                // dL/dK[n][m] * K
+                const double Psym = gK - gr[a * bf + m] * bn * K;          // (gK + gK^T)[n][m] * K
+#pragma unroll
+                for (int d = 0; d < MAXD; ++d) {
+                    accx[d] = fma(-Psym * il2[d], diff[d], accx[d]);
+                    accl[d] = fma(gK, diff[d] * diff[d], accl[d]);
+                }
             }
+#pragma unroll
+            for (int d = 0; d < MAXD; ++d) if (d < Ds) gX[(size_t)r * bf * Ds + n * Ds + d] += accx[d];
         }
-        gX[(size_t)r * bf * Ds + e] += acc;
-    }
-    for (int e = tid; e < U * Ds; e += nt) {
-        const int a = e / Ds, d = e % Ds;
-        double acc = 0.0;
-        for (int n = 0; n < bf; ++n)
-            for (int m = 0; m < bf; ++m) {
-                double d2 = 0.0;
-                for (int k = 0; k < Ds; ++k) { const double tt = (Xr[n * Ds + k] - Xr[m * Ds + k]) / lr[a * Ds + k]; d2 = fma(tt, tt, d2); }
-                const double diff = Xr[n * Ds + d] - Xr[m * Ds + d];
-                acc = fma(-gr[a * bf + n] * br[a * bf + m] * exp(-0.5 * d2), diff * diff, acc);
-            }
-        const double l = lr[a * Ds + d];
-        gell[(size_t)r * U * Ds + e] += acc / (l * l * l);
+        block_sum<MAXD>(accl, MAXD, sgl, sglo);
+        if (tid < Ds) { const double l = lr[a * Ds + tid]; gell[(size_t)r * U * Ds + a * Ds + tid] += sglo[tid] / (l * l * l); }
+        __syncthreads();
     }
 }
 
