@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--restarts", type=int, default=32, help="policy restarts per GPU")
     ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward extra line")
-    ap.add_argument("--nsplit", type=int, default=4, help="sub-batches on parallel streams inside the captured graph")
+    ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
