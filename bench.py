@@ -26,6 +26,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 must print exactly ONE line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 CFG = dict(N=300, Ds=10, U=2, H=40, bf=50)
 METRIC = "moment-match rollout steps/sec (N=300, E=10, H=40, fp64)"
