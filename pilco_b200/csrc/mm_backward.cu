@@ -62,9 +62,14 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 3) mm_btile_kernel(MMBwdParams
     tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < p.gp.n, lane, ua, Apv);
     const double* ikrow = DIAG ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
 
-    double accL[DP + 1], accK[DIAG ? DP + 1 : 1];
+    // accumulators: row sums hL (hK) per lane (quad-reduced at the end) and HV in DMMA C-fragment layout:
+    // hv[nt][c] = HV[row g][8 nt + 2t + c], complete sums over the columns (the DMMA reduces over k = column)
+    constexpr int NT = (DP + 7) / 8;
+    double hl = 0.0, hk = 0.0;
+    double hvL[NT][2], hvK[DIAG ? NT : 1][2];
 #pragma unroll
-    for (int i = 0; i <= DP; ++i) { accL[i] = 0.0; if (DIAG) accK[i] = 0.0; }
+    for (int nt = 0; nt < NT; ++nt) { hvL[nt][0] = hvL[nt][1] = 0.0; if (DIAG) { hvK[nt][0] = hvK[nt][1] = 0.0; } }
+    const int qb = lane & ~3;                              // first lane of this quad
     unsigned phase = 0;
     for (int c0 = 0; c0 < ncol8; c0 += CM) {
         const int cm = (np - c0) < CM ? (np - c0) : CM;
@@ -86,46 +91,54 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 3) mm_btile_kernel(MMBwdParams
                 }
                 const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
                 const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
-                const double w0 = bb.x * l0, w1 = bb.y * l1;
+                const double w0 = bb.x * l0, w1 = bb.y * l1;        // W[g][2t], W[g][2t+1]  (C-fragment layout)
+                hl += w0 + w1;
                 double v0 = 0.0, v1 = 0.0;
                 if (DIAG) {
                     const double2 ik = *reinterpret_cast<const double2*>(ikrow + c0 + col + 2 * t);
                     v0 = ik.x * l0; v1 = ik.y * l1;
-                    accK[DP] += v0 + v1;
+                    hk += v0 + v1;
                 }
-                const double* z0 = sZ + (size_t)(col + 2 * t) * ldz;
-                const double* z1 = z0 + ldz;
-                accL[DP] += w0 + w1;
+                // HV[8 x DP] += W[8 x 8] . zeta[col : col+8, 0:DP]  as 2 k-steps x NT n-tiles of DMMA
 #pragma unroll
-                for (int d = 0; d < DP; d += 2) {
-                    const double2 za = *reinterpret_cast<const double2*>(z0 + d);
-                    const double2 zb = *reinterpret_cast<const double2*>(z1 + d);
-                    accL[d] = fma(w0, za.x, fma(w1, zb.x, accL[d]));
-                    accL[d + 1] = fma(w0, za.y, fma(w1, zb.y, accL[d + 1]));
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    // A fragment: W[g][4 k2 + t], held by quad lane 2 k2 + (t >> 1) as element t & 1
+                    const int src = qb | (2 * k2 + (t >> 1));
+                    const double x0 = __shfl_sync(0xffffffffu, w0, src), x1 = __shfl_sync(0xffffffffu, w1, src);
+                    const double aw = (t & 1) ? x1 : x0;
+                    double ak = 0.0;
                     if (DIAG) {
-                        accK[d] = fma(v0, za.x, fma(v1, zb.x, accK[d]));
-                        accK[d + 1] = fma(v0, za.y, fma(v1, zb.y, accK[d + 1]));
+                        const double y0 = __shfl_sync(0xffffffffu, v0, src), y1 = __shfl_sync(0xffffffffu, v1, src);
+                        ak = (t & 1) ? y1 : y0;
+                    }
+                    const double* zrow = sZ + (size_t)(col + 4 * k2 + t) * ldz;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double bz = (8 * nt + g < DP) ? zrow[8 * nt + g] : 0.0;     // B[k = col][n = d]
+                        dmma884(hvL[nt][0], hvL[nt][1], aw, bz);
+                        if (DIAG) dmma884(hvK[nt][0], hvK[nt][1], ak, bz);
                     }
                 }
             }
         }
     }
-    // quad reduction (4 lanes share a row), then the quad writes the row's outputs
-    // layout: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK  (hK/HVK only for DIAG pairs)
+    // outputs per row: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK  (hK/HVK only for DIAG pairs)
     double* out = wsr + bp.B.rowout + ((size_t)q * np + row) * bp.B.ldr;
+    hl += __shfl_xor_sync(0xffffffffu, hl, 1);
+    hl += __shfl_xor_sync(0xffffffffu, hl, 2);
+    if (t == 0) out[0] = active ? hl : 0.0;
+    if (DIAG) {
+        hk += __shfl_xor_sync(0xffffffffu, hk, 1);
+        hk += __shfl_xor_sync(0xffffffffu, hk, 2);
+        if (t == 0) out[DP + 1] = active ? hk : 0.0;
+    }
 #pragma unroll
-    for (int i = 0; i <= DP; ++i) {
-        double v = accL[i];
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        const int slotL = (i == DP) ? 0 : 1 + i;
-        if ((i & 3) == t) out[slotL] = active ? v : 0.0;
-        if (DIAG) {
-            double k = accK[i];
-            k += __shfl_xor_sync(0xffffffffu, k, 1);
-            k += __shfl_xor_sync(0xffffffffu, k, 2);
-            const int slotK = (i == DP) ? DP + 1 : DP + 2 + i;
-            if ((i & 3) == t) out[slotK] = active ? k : 0.0;
+    for (int nt = 0; nt < NT; ++nt) {
+        const int d0 = 8 * nt + 2 * t;
+        if (d0 < DP) {
+            out[1 + d0] = active ? hvL[nt][0] : 0.0;
+            out[2 + d0] = active ? hvL[nt][1] : 0.0;
+            if (DIAG) { out[DP + 2 + d0] = active ? hvK[nt][0] : 0.0; out[DP + 3 + d0] = active ? hvK[nt][1] : 0.0; }
         }
     }
 }
