@@ -98,6 +98,18 @@ int pilco_gp_factorize(int n, int D, int E, int B,
                        int* info,                            /* [B] or NULL */
                        void* ws, size_t ws_bytes, pilco_stream_t stream);
 
+/* GP training objective: nlml[b,e] = -log p(y_e | X, theta_be) and its gradient w.r.t. the
+ * constrained hyper-parameters, batched over B hyper-parameter sets x E outputs.  Replaces
+ * gpflow.models.GPR.training_loss + TF autodiff inside MGPR.optimize (pilco/models/mgpr.py:47-75); the Gamma priors
+ * of mgpr.py:33-34 are added by the host.  Outputs nlml [B,E], g_ell [B,E,D], g_sf2 [B,E], g_sn2 [B,E]. */
+size_t pilco_gp_nlml_workspace_bytes(int n, int E, int B);
+int pilco_gp_nlml(int n, int D, int E, int B,
+                  const double* X,   long long X_bs, const double* Y,   long long Y_bs,
+                  const double* ell, long long ell_bs, const double* sf2, long long sf2_bs,
+                  const double* sn2, long long sn2_bs,
+                  double* nlml, double* g_ell, double* g_sf2, double* g_sn2, int* info,
+                  void* ws, size_t ws_bytes, pilco_stream_t stream);
+
 /* Replaces SMGPR.calculate_factorizations (pilco/models/smgpr.py:24-45; gp1.m:52-82): FITC over
  * Mi inducing points Z.  Outputs iK[E,ldk,ldk] (zero padded) and beta[E,Mi].
  * ws: scratch of pilco_fitc_workspace_bytes(N, Mi, E) bytes. */

@@ -438,6 +438,87 @@ int pilco_gp_factorize(int n, int D, int E, int B,
     return PILCO_OK;
 }
 
+// ---- GP training objective: -log p(y | X, theta) and its gradient w.r.t. (ell, sf2, sn2) ------------------------
+// Replaces gpflow.models.GPR.training_loss + TF autodiff as used by MGPR.optimize (pilco/models/mgpr.py:47-75;
+// priors are added on the host).  d/dtheta = -0.5 tr((alpha alpha^T - K^-1) dK/dtheta).
+__global__ void __launch_bounds__(256) gp_nlml_grad_kernel(int n, int D, int E, const double* X, long long X_bs,
+                                                           const double* Y, long long Y_bs,
+                                                           const double* ell, long long ell_bs,
+                                                           const double* sf2, long long sf2_bs,
+                                                           const double* Lall, const double* iKall, int ldw,
+                                                           const double* alpha,
+                                                           double* nlml, double* g_ell, double* g_sf2, double* g_sn2) {
+    const int z = blockIdx.x, bidx = z / E, e = z % E;
+    const int tid = threadIdx.x;
+    const double* Xb = X + (size_t)bidx * X_bs;
+    const double* Yb = Y + (size_t)bidx * Y_bs;
+    const double* le = ell + (size_t)bidx * ell_bs + (size_t)e * D;
+    const double sf = sf2[(size_t)bidx * sf2_bs + e];
+    const double* L = Lall + (size_t)z * ldw * ldw;
+    const double* iK = iKall + (size_t)z * ldw * ldw;
+    const double* al = alpha + (size_t)z * n;
+    __shared__ double sred[(MAXD + 4) * 8], sout[MAXD + 4];
+    double il[MAXD];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) il[d] = d < D ? 1.0 / le[d] : 0.0;
+    double acc[MAXD + 3];                    // [0..D): ell, [MAXD]: sf2, [MAXD+1]: sn2, [MAXD+2]: nlml pieces
+#pragma unroll
+    for (int i = 0; i < MAXD + 3; ++i) acc[i] = 0.0;
+    for (int idx = tid; idx < n * n; idx += blockDim.x) {
+        const int i = idx / n, j = idx % n;
+        double d2 = 0.0, df[MAXD];
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) {
+            df[d] = d < D ? (Xb[(size_t)i * D + d] - Xb[(size_t)j * D + d]) * il[d] : 0.0;
+            d2 = fma(df[d], df[d], d2);
+        }
+        const double Kf = sf * exp(-0.5 * d2);
+        const double W = al[i] * al[j] - iK[(size_t)i * ldw + j];
+        const double t = W * Kf;
+        acc[MAXD] += t;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) acc[d] = fma(t, df[d] * df[d], acc[d]);    // (x_i-x_j)^2/ell^2 ; /ell below
+        if (i == j) acc[MAXD + 1] += W;
+    }
+    for (int i = tid; i < n; i += blockDim.x)
+        acc[MAXD + 2] += 0.5 * Yb[(size_t)i * E + e] * al[i] + log(L[(size_t)i * ldw + i]);
+    block_sum<MAXD + 3>(acc, MAXD + 3, sred, sout);
+    if (tid < D) g_ell[(size_t)z * D + tid] = -0.5 * sout[tid] * il[tid];       // dK/dell_d = K (x-x')^2 / ell^3
+    if (tid == 0) {
+        g_sf2[z] = -0.5 * sout[MAXD] / sf;
+        g_sn2[z] = -0.5 * sout[MAXD + 1];
+        nlml[z] = sout[MAXD + 2] + 0.5 * n * 1.8378770664093453;               // log(2 pi)
+    }
+}
+
+size_t pilco_gp_nlml_workspace_bytes(int n, int E, int B) {
+    if (n < 1 || E < 1 || B < 1) return 0;
+    const size_t ldw = pad64(n);
+    return pilco_gp_factorize_workspace_bytes(n, E, B) + ((size_t)B * E * (ldw * ldw + ldw)) * sizeof(double);
+}
+
+int pilco_gp_nlml(int n, int D, int E, int B,
+                  const double* X, long long X_bs, const double* Y, long long Y_bs,
+                  const double* ell, long long ell_bs, const double* sf2, long long sf2_bs,
+                  const double* sn2, long long sn2_bs,
+                  double* nlml, double* g_ell, double* g_sf2, double* g_sn2, int* info,
+                  void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    if (!nlml || !g_ell || !g_sf2 || !g_sn2 || !ws) return PILCO_ERR_NULL;
+    if (ws_bytes < pilco_gp_nlml_workspace_bytes(n, E, B)) return PILCO_ERR_WORKSPACE;
+    const size_t fbytes = pilco_gp_factorize_workspace_bytes(n, E, B);
+    const int ldw = pad64(n);
+    double* fws = (double*)ws;
+    double* iK = (double*)((char*)ws + fbytes);
+    double* alpha = iK + (size_t)B * E * ldw * ldw;
+    int rc = pilco_gp_factorize(n, D, E, B, X, X_bs, Y, Y_bs, ell, ell_bs, sf2, sf2_bs, sn2, sn2_bs,
+                                iK, ldw, alpha, info, fws, fbytes, stream);
+    if (rc) return rc;
+    gp_nlml_grad_kernel<<<B * E, 256, 0, (cudaStream_t)stream>>>(n, D, E, X, X_bs, Y, Y_bs, ell, ell_bs, sf2, sf2_bs,
+                                                                 fws, iK, ldw, alpha, nlml, g_ell, g_sf2, g_sn2);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
 size_t pilco_fitc_workspace_bytes(int N, int Mi, int E) {
     if (N < 1 || Mi < 1 || E < 1) return 0;
     const size_t ldm = pad64(Mi) + 64, ldn = pad64(N);

@@ -20,7 +20,7 @@ static inline __host__ __device__ size_t mm_btile_smem_bytes(int np, int ldz) {
 // DIAG = true : grid (NB, E, R), the pairs (a,a) of a GP with trace term (iK-weighted sums as well);
 // DIAG = false: grid (NB, E*E, R), every other ordered pair (CTAs of (a,a) pairs that DIAG handles exit at once).
 template <int KS, bool DIAG>
-__global__ void __launch_bounds__(256, DIAG ? 2 : 3) mm_btile_kernel(MMBwdParams bp) {
+__global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams bp) {
     constexpr int DP = 4 * KS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMParams& p = bp.f;

@@ -105,6 +105,38 @@ def gp_refactorize(gp):
                                  ptr(gp.info), ptr(gp.fact_ws), wsb, stream_ptr()), "gp_factorize")
 
 
+class GpNlml:
+    """pilco_gp_nlml with persistent buffers: -log p(y_e | X, theta) and gradients for B hyper-parameter sets."""
+
+    def __init__(self, X, Y, B):
+        d = device()
+        self.X, self.Y = dev(X), dev(Y)
+        self.n, self.D = self.X.shape
+        self.E, self.B = self.Y.shape[1], int(B)
+        B, E, D = self.B, self.E, self.D
+        self.ell = torch.empty((B, E, D), dtype=F64, device=d)
+        self.sf2 = torch.empty((B, E), dtype=F64, device=d)
+        self.sn2 = torch.empty((B, E), dtype=F64, device=d)
+        self.out = torch.empty((B, E, D + 3), dtype=F64, device=d)       # [g_ell | g_sf2 | g_sn2 | nlml]
+        self.nlml = torch.empty((B, E), dtype=F64, device=d)
+        self.g_ell = torch.empty((B, E, D), dtype=F64, device=d)
+        self.g_sf2 = torch.empty((B, E), dtype=F64, device=d)
+        self.g_sn2 = torch.empty((B, E), dtype=F64, device=d)
+        self.info = torch.zeros(B, dtype=torch.int32, device=d)
+        self.wsb = lib.pilco_gp_nlml_workspace_bytes(self.n, E, B)
+        self.ws = torch.empty(self.wsb // 8, dtype=F64, device=d)
+
+    def __call__(self, ell, sf2, sn2):
+        """numpy [B,E,D], [B,E], [B,E] -> nlml [B,E], g_ell [B,E,D], g_sf2 [B,E], g_sn2 [B,E], bad [B] (numpy)"""
+        self.ell.copy_(torch.as_tensor(ell)); self.sf2.copy_(torch.as_tensor(sf2)); self.sn2.copy_(torch.as_tensor(sn2))
+        n, D, E, B = self.n, self.D, self.E, self.B
+        check(lib.pilco_gp_nlml(n, D, E, B, ptr(self.X), 0, ptr(self.Y), 0, ptr(self.ell), E * D, ptr(self.sf2), E,
+                                ptr(self.sn2), E, ptr(self.nlml), ptr(self.g_ell), ptr(self.g_sf2), ptr(self.g_sn2),
+                                ptr(self.info), ptr(self.ws), self.wsb, stream_ptr()), "gp_nlml")
+        return (self.nlml.cpu().numpy(), self.g_ell.cpu().numpy(), self.g_sf2.cpu().numpy(), self.g_sn2.cpu().numpy(),
+                self.info.cpu().numpy() != 0)
+
+
 def fitc_factorize(X, Z, Y, ell, sf2, sn2):
     """pilco_fitc_factorize: FITC over inducing points Z -> DeviceGP centred on Z."""
     X, Z, Y, ell, sf2, sn2 = dev(X), dev(Z), dev(Y), dev(ell), dev(sf2), dev(sn2)

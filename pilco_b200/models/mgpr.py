@@ -105,8 +105,15 @@ class MGPR:
                 model.data = (np.asarray(data[0], dtype=np.float64), np.asarray(data[1][:, i:i + 1], dtype=np.float64))
         self.num_datapoints = np.asarray(data[0]).shape[0]
 
-    # ---- training (mgpr.py:47-75; host logic, see gp_training.py) ----------------------------
+    # ---- training (mgpr.py:47-75) -----------------------------------------------------------------
     def optimize(self, restarts=1, maxiter=None):
+        """All outputs and restarts in lock step on the device (pilco_gp_nlml; gp_device_training.py)."""
+        from .. import gp_device_training
+        self.optimizers = [True] * len(self.models)
+        return gp_device_training.optimize_mgpr(self, restarts=restarts, maxiter=maxiter)
+
+    def optimize_host(self, restarts=1, maxiter=None):
+        """Host path (torch-CPU autograd + SciPy): used by SMGPR (FITC objective, gp_training.py)."""
         for model in self.models:
             model.optimize(maxiter)
         self.optimizers = [True] * len(self.models)

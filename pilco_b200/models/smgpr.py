@@ -44,6 +44,10 @@ class SMGPR(MGPR):
             Z = np.random.rand(self.num_induced_points, self.num_dims)      # smgpr.py:20
             self.models.append(GPRFITCModel((data[0], data[1][:, i:i + 1]), kern, Z))
 
+    def optimize(self, restarts=1, maxiter=None):
+        """FITC objective with trainable inducing inputs: host logic (gp_training.fitc_loss), see DESIGN.md section 9."""
+        return self.optimize_host(restarts=restarts, maxiter=maxiter)
+
     @property
     def Z(self):
         return self.models[0].inducing_variable.Z                           # smgpr.py:50-52

@@ -61,19 +61,20 @@ def test_parameter_surface():
 
 
 def test_gp_training_reduces_loss_and_restarts_keep_best():
+    """host training driver (the SMGPR / FITC path and the reference for the device NLML kernel)"""
     from pilco.models import MGPR
     np.random.seed(0)
     X = np.random.rand(40, 2)
     Y = np.sin(3 * X).dot(np.random.rand(2, 1)) + 1e-2 * np.random.randn(40, 1)
     m = MGPR((X, Y))
     l0 = m.models[0].training_loss()
-    m.optimize(restarts=1)
+    m.optimize_host(restarts=1)
     l1 = m.models[0].training_loss()
     assert l1 < l0 and np.all(m.lengthscales > 0) and np.all(m.noise >= 1e-6)
     m.models[0].likelihood.variance.assign(0.01)
     from gpflow import set_trainable
     set_trainable(m.models[0].likelihood.variance, False)
-    m.optimize(restarts=0)
+    m.optimize_host(restarts=0)
     assert abs(m.noise[0] - 0.01) < 1e-12
 
 
@@ -84,6 +85,8 @@ def test_smgpr_and_controller_host_surface():
     X = np.random.rand(30, 3); Y = np.random.rand(30, 2)
     s = SMGPR((X, Y), num_induced_points=7)
     assert s.Z.numpy().shape == (7, 3) and s.centres.shape == (7, 3)
+    s.optimize(restarts=0, maxiter=5)                                  # FITC training stays on the host
+    assert np.all(s.lengthscales > 0)
     rbf = RbfController(3, 2, 11, max_action=2.0)
     assert rbf.models[1].X is rbf.models[0].X                          # shared centres (controllers.py:103-106)
     assert not rbf.models[0].kernel.variance.trainable and not rbf.models[0].likelihood.variance.trainable
