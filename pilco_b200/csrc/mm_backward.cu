@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
 #define BF_CHUNK 128
 
 template <int DP>
-__global__ void __launch_bounds__(128) mm_bfinish_kernel(MMBwdParams bp) {
+__global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
     const MMParams& p = bp.f;
     const pilco_gp_model& gp = p.gp;
     const MMBws& B = bp.B;

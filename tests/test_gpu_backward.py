@@ -83,7 +83,7 @@ def test_rollout_gradient_matches_autograd(kind, R):
             ps = [T(Xc[r]).requires_grad_(), T(Yc[r]).requires_grad_(), T(lc[r]).requires_grad_()]
         total = _torch_rollout_reward(kind, ps, X, Y, ell, sf2, sn2, maxa, Wr, tr, m0, S0, H)
         grads = torch.autograd.grad(total, ps)
-        assert abs(float(reward[r]) - float(total)) < 1e-9
+        assert abs(float(reward[r]) - float(total.detach())) < 1e-9
         names = ["W", "b"] if kind == "linear" else ["X", "Y", "ell"]
         for nm, ref in zip(names, grads):
             err = scaled_err(g[nm][r].cpu().numpy(), ref.numpy())
@@ -105,9 +105,9 @@ def test_recipe_cascade_with_policy_optimisation():
     pilco = PILCO((X0, Y0))
     pilco.controller.max_action = e
     pilco.optimize_models(restarts=2)
-    r0 = float(pilco.compute_reward())
+    r0 = float(np.asarray(pilco.compute_reward()).item())
     pilco.optimize_policy(restarts=5)
-    r1 = float(pilco.compute_reward())
+    r1 = float(np.asarray(pilco.compute_reward()).item())
     assert r1 >= r0 - 1e-9, "policy optimisation must not decrease the expected reward (%g -> %g)" % (r0, r1)
     m = np.random.rand(1, d)
     s = np.random.rand(d, d)
@@ -138,9 +138,9 @@ def test_rbf_policy_optimisation_improves_reward():
     for mod in pilco.mgpr.models:
         mod.likelihood.variance.assign(1e-3)
         mod.kernel.lengthscales.assign(np.ones(Ds + U) * 2.0)
-    r0 = float(pilco.compute_reward())
+    r0 = float(np.asarray(pilco.compute_reward()).item())
     pilco.optimize_policy(maxiter=15, restarts=3)
-    r1 = float(pilco.compute_reward())
+    r1 = float(np.asarray(pilco.compute_reward()).item())
     assert np.isfinite(r1) and r1 >= r0 - 1e-9
 
 

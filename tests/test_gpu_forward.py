@@ -253,4 +253,4 @@ def test_rollout_matches_python_port(kind, R):
         Mr, Sr, Rr = pp.predict(m0[None], S0, H, acts[r], dyn, rfn)
         assert scaled_err(tm[r, -1].cpu().numpy(), Mr[0]) < 1e-8
         assert scaled_err(tS[r, -1].cpu().numpy(), Sr) < 1e-7
-        assert abs(float(rew[r]) - float(Rr)) < 1e-8 * max(1.0, abs(float(Rr)))
+        assert abs(float(rew[r]) - Rr.item()) < 1e-8 * max(1.0, abs(Rr.item()))
