@@ -34,7 +34,7 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     L.zeta = o;  o += (size_t)L.np * L.ldz;
     L.betap = o; o += (size_t)E * L.np;
     L.Bq = o;    o += (size_t)L.P * L.np;
-    L.Tpart = o; o += (size_t)L.P * L.NB;
+    L.Tpart = o; o += (size_t)L.P * (L.np / 8);
     o = (o + 1) & ~(size_t)1;
     L.Wm = o;    o += (size_t)E * MAXD * MAXD;          // setup stage 1 -> 2: W_a
     L.Wc = o;    o += (size_t)((E + 1) & ~1);           //                      c_a
@@ -478,10 +478,13 @@ static inline __host__ __device__ size_t mm_tile_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
     return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
 }
-static inline __host__ __device__ int mm_tile_slots(int np) { return np / 64; }
+// one partial per row octet (= per warp of a tile CTA): warps retire independently, no block reduction
+static inline __host__ __device__ int mm_tile_slots(int np) { return np / 8; }
 
-template <int KS, int MINB>
-__global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
+// Body of one tile CTA, specialised on the pair kind so that off-diagonal pairs carry neither the
+// triangle bookkeeping nor the (predicated-off but still issued) trace FMAs of the diagonal pairs.
+template <int KS, bool SYM, bool DIAG>
+__device__ __forceinline__ void mm_tile_body(const MMParams& p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMWs& L = p.L;
     const int np = L.np, ldz = L.ldz, n = p.gp.n;
@@ -502,13 +505,12 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
     const int row = row0 + g;
     const bool active = row0 < n;                      // warp-uniform
     const int ncol8 = (n + 7) & ~7;                    // columns at or beyond this are pure padding
-    const bool sympair = (a == b);                     // symmetric pair: visit the upper triangle only
-    const bool diag = sympair && (p.gp.mode == 0) && (p.gp.iK != nullptr);
+    constexpr bool sympair = SYM;                      // symmetric pair (a == b): visit the upper triangle only
+    constexpr bool diag = DIAG;                        // ... and (exact-GP mode) subtract the trace term
     // first column this CTA needs (symmetric pairs skip everything left of its first row tile)
     const int cfirst = sympair ? rb * 64 : 0;
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
-    __syncthreads();                                    // barrier initialised (nothing else precedes: cheap)
 
     // stage one column chunk (zeta rows, B_q, beta_b) and, with the first chunk, the exp table
     auto issue_chunk = [&](int c0, bool with_table) {
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
     tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < n, lane, ua, Apv);
     const double ba = wsr[L.betap + (size_t)a * np + row];
     const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+    __syncthreads();                                    // barrier initialisation visible to the waiting warps
 
     double acc2 = 0.0, accd = 0.0, tr2 = 0.0, trd = 0.0;   // strictly-upper / diagonal-tile accumulators
     unsigned phase = 0;
@@ -615,14 +618,17 @@ __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
     double v = (t == 0) ? ba * acc : 0.0;
     v = warp_sum(v);
     tr = warp_sum(tr);
-    __shared__ double sred[8];
-    if (lane == 0) sred[warp] = active ? (v - tr) : 0.0;
-    __syncthreads();
-    if (tid == 0) {
-        double tot = 0.0;
-        for (int w = 0; w < 8; ++w) tot += sred[w];
-        p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * L.NB + rb] = tot;
-    }
+    if (lane == 0)
+        p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * mm_tile_slots(np) + rb * 8 + warp] = active ? (v - tr) : 0.0;
+}
+
+template <int KS, int MINB>
+__global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
+    int a, b;
+    pair_decode(blockIdx.y, a, b);
+    if (a != b) mm_tile_body<KS, false, false>(p);
+    else if (p.gp.mode == 0 && p.gp.iK != nullptr) mm_tile_body<KS, true, true>(p);
+    else mm_tile_body<KS, true, false>(p);
 }
 
 // -------------------------------------------------------------------------------------------------
