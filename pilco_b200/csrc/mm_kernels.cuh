@@ -487,7 +487,8 @@ template <int KS, bool SYM, bool DIAG>
 __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMWs& L = p.L;
-    const int np = L.np, ldz = L.ldz, n = p.gp.n;
+    constexpr int ldz = KS == 1 ? 4 : (KS <= 3 ? 12 : 20);    // == ldz_of(D) for every D with ksteps_of(D) == KS
+    const int np = L.np, n = p.gp.n;
     const int CM = np < TILE_CM ? np : TILE_CM;
     double* sZ = reinterpret_cast<double*>(smem_raw);
     double* sBq = sZ + (size_t)CM * ldz;
@@ -529,7 +530,10 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
     // row operands are computed while the copies are in flight
     double ua[KS], Apv;
     tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < n, lane, ua, Apv);
-    const double ba = wsr[L.betap + (size_t)a * np + row];
+    // integer part of A' rides in the rounding constant of the exp, the fractional part scales the row sums
+    double am, rowfac;
+    exp_row_split(Apv, am, rowfac);
+    const double ba = wsr[L.betap + (size_t)a * np + row] * rowfac;
     const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
     __syncthreads();                                    // barrier initialisation visible to the waiting warps
 
@@ -564,7 +568,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const double2 bq = *reinterpret_cast<const double2*>(sBq + cg + 8 * j + 2 * t);
-                        e[2 * j] = Apv + bq.x; e[2 * j + 1] = Apv + bq.y;
+                        e[2 * j] = bq.x; e[2 * j + 1] = bq.y;
                     }
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
@@ -576,7 +580,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double l0 = exp_scaled(e[2 * j], tab), l1 = exp_scaled(e[2 * j + 1], tab);
+                        const double l0 = exp_shifted(e[2 * j], am, tab), l1 = exp_shifted(e[2 * j + 1], am, tab);
                         const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
                         acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
                         if (diag) { tr2 = fma(ik[j].x, l0, tr2); tr2 = fma(ik[j].y, l1, tr2); }
@@ -589,13 +593,13 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
                     const int gcol = c0 + col;
                     if (col < cend && (!sympair || gcol >= row0)) {         // warp-uniform
                         const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
-                        double e0 = Apv + bq.x, e1 = Apv + bq.y;
+                        double e0 = bq.x, e1 = bq.y;
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
                             const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
                             dmma884(e0, e1, ua[ks], bf);
                         }
-                        const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
+                        const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
                         const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                         const double2 ikj = diag ? *reinterpret_cast<const double2*>(ikrow + gcol + 2 * t) : make_double2(0.0, 0.0);
                         if (sympair && gcol == row0) {
@@ -617,7 +621,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     double v = (t == 0) ? ba * acc : 0.0;
     v = warp_sum(v);
-    tr = warp_sum(tr);
+    tr = warp_sum(tr * rowfac);
     if (lane == 0)
         p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * mm_tile_slots(np) + rb * 8 + warp] = active ? (v - tr) : 0.0;
 }
