@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PILCO_ABI_VERSION 1
+#define PILCO_ABI_VERSION 2
 #define PILCO_MAX_D 16          /* max GP input dimension (state+control) */
 #define PILCO_MAX_E 16          /* max number of GP outputs */
 
@@ -144,6 +144,15 @@ int pilco_exp_reward(int Ds, int R, const double* W /*[Ds,Ds]*/, const double* t
                      double* muR /*[R]*/, double* sR /*[R] or NULL*/, int* info,
                      pilco_stream_t stream);
 
+/* Safe-PILCO risk rewards (safe_pilco_extension/rewards_safe.py:13-58: RiskOfCollision.compute_reward,
+ * SingleConstraint.compute_reward): probability that the constrained state dimensions lie inside a box,
+ * each dimension an independent univariate normal with loc m[d] and scale sfac*s[d,d] (as the reference
+ * writes it).  prm (device, doubles) = [nd, inside, sfac, (dim_k, low_k, high_k) x nd]; a missing bound is
+ * +-inf; inside = 0 returns the complement.  Optional d risk/d m [R,Ds] and d risk/d diag(s) [R,Ds]. */
+int pilco_box_risk(int Ds, int R, const double* prm, const double* m /*[R,Ds]*/, const double* s /*[R,Ds,Ds]*/,
+                   double* risk /*[R]*/, double* drisk_dm /*[R,Ds] or NULL*/, double* drisk_dv /*[R,Ds] or NULL*/,
+                   pilco_stream_t stream);
+
 /* ---- H-step rollout ---------------------------------------------------------------------------
  * Replaces PILCO.predict / PILCO.propagate (pilco/models/pilco.py:118-153; pred.m:29-39,
  * propagate.m:33-85): policy moments -> joint state/action Gaussian -> dynamics moment match ->
@@ -153,6 +162,13 @@ int pilco_exp_reward(int Ds, int R, const double* W /*[Ds,Ds]*/, const double* t
 #define PILCO_POLICY_RBF    1
 #define PILCO_REWARD_EXP    0
 #define PILCO_REWARD_LINEAR 1
+#define PILCO_REWARD_BOX    2   /* pilco_box_risk; W = its prm block, t unused */
+/* accumulation channel of a reward term (safe_pilco_extension/safe_pilco.py:29-50, SafePILCO.predict):
+ *   ADD : reward_add  += coef * value(x_t)                       (PILCO.predict, pilco.py:130-134)
+ *   MULT: reward_mult *= 1 - sum_k coef_k * value_k(x_t)          (the terms of this channel form the risk)
+ * and the rollout returns  reward = reward_add + mult_mu * (1 - reward_mult). */
+#define PILCO_CHANNEL_ADD   0
+#define PILCO_CHANNEL_MULT  1
 
 typedef struct pilco_policy {
     int kind;                   /* PILCO_POLICY_* */
@@ -168,8 +184,9 @@ typedef struct pilco_policy {
 
 typedef struct pilco_reward_term {
     int kind;                   /* PILCO_REWARD_* */
+    int channel;                /* PILCO_CHANNEL_* */
     double coef;                /* CombinedRewards weight (rewards.py:64-81) */
-    const double* W;            /* exp: [Ds,Ds]; linear: [Ds] */
+    const double* W;            /* exp: [Ds,Ds]; linear: [Ds]; box: prm block */
     const double* t;            /* exp: [Ds] target; linear: unused */
 } pilco_reward_term;
 
@@ -184,10 +201,12 @@ typedef struct pilco_rollout {
     /* outputs */
     double* traj_m;             /* [R,H+1,Ds]    state means, t=0..H   */
     double* traj_S;             /* [R,H+1,Ds,Ds] state covariances      */
-    double* reward;             /* [R] sum_{t<H} E[r(x_t)]              */
+    double* reward;             /* [R] sum_{t<H} E[r(x_t)]  (+ mult_mu (1 - prod_t (1 - risk_t)))  */
     double* step_reward;        /* [R,H] or NULL                        */
     int* info;                  /* [R]                                   */
     void* ws; size_t ws_bytes;
+    double mult_mu;             /* SafePILCO.mu (safe_pilco.py:26,49); ignored without MULT terms */
+    double* step_risk;          /* [R,H] per-step risk of the MULT channel, or NULL */
 } pilco_rollout;
 
 size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro);

@@ -33,7 +33,7 @@ class Policy(C.Structure):
 
 class RewardTerm(C.Structure):
     """mirror of ``pilco_reward_term``"""
-    _fields_ = [("kind", C.c_int), ("coef", C.c_double), ("W", c_dp), ("t", c_dp)]
+    _fields_ = [("kind", C.c_int), ("channel", C.c_int), ("coef", C.c_double), ("W", c_dp), ("t", c_dp)]
 
 
 class Rollout(C.Structure):
@@ -43,7 +43,8 @@ class Rollout(C.Structure):
                 ("n_rewards", C.c_int), ("rewards", RewardTerm * 8),
                 ("m0", c_dp), ("m0_bs", c_ll), ("S0", c_dp), ("S0_bs", c_ll),
                 ("traj_m", c_dp), ("traj_S", c_dp), ("reward", c_dp), ("step_reward", c_dp),
-                ("info", c_dp), ("ws", c_dp), ("ws_bytes", C.c_size_t)]
+                ("info", c_dp), ("ws", c_dp), ("ws_bytes", C.c_size_t),
+                ("mult_mu", C.c_double), ("step_risk", c_dp)]
 
 
 class RolloutGrad(C.Structure):
@@ -53,7 +54,9 @@ class RolloutGrad(C.Structure):
 
 
 POLICY_LINEAR, POLICY_RBF = 0, 1
-REWARD_EXP, REWARD_LINEAR = 0, 1
+REWARD_EXP, REWARD_LINEAR, REWARD_BOX = 0, 1, 2
+CHANNEL_ADD, CHANNEL_MULT = 0, 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); every symbol declared in include/pilco_b200.h
 SIGNATURES = {
@@ -74,6 +77,7 @@ SIGNATURES = {
     "pilco_squash_sin": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 7),
     "pilco_linear_action": (C.c_int, [C.c_int] * 3 + [c_dp, c_ll, c_dp, c_ll] + [c_dp] * 6),
     "pilco_exp_reward": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 8),
+    "pilco_box_risk": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 7),
     "pilco_rollout_workspace_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
     "pilco_rollout_forward": (C.c_int, [C.POINTER(Rollout), c_dp]),
     "pilco_mm_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
@@ -96,7 +100,7 @@ def _load():
         fn = getattr(lib, name)          # AttributeError if the .so does not export the symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.pilco_version() != 1:
+    if lib.pilco_version() != ABI_VERSION:
         raise RuntimeError("pilco_b200: ABI version mismatch")
     return lib
 

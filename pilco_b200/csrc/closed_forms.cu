@@ -28,6 +28,24 @@ __global__ void __launch_bounds__(128) exp_reward_kernel(int Ds, const double* W
     if (threadIdx.x == 0) muR[r] = mu;
 }
 
+__global__ void __launch_bounds__(32) box_risk_kernel(int Ds, const double* prm, const double* m, const double* s,
+                                                      double* risk, double* dmo, double* dvo) {
+    const size_t r = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    double dm[RISK_MAX_DIMS], dv[RISK_MAX_DIMS];
+    const bool grad = dmo != nullptr || dvo != nullptr;
+    risk[r] = risk_box_eval(Ds, prm, m + r * Ds, s + r * Ds * Ds, grad ? dm : nullptr, grad ? dv : nullptr);
+    if (grad) {
+        for (int i = 0; i < Ds; ++i) { if (dmo) dmo[r * Ds + i] = 0.0; if (dvo) dvo[r * Ds + i] = 0.0; }
+        const int nd = (int)prm[0];
+        for (int k = 0; k < nd; ++k) {
+            const int d = (int)prm[3 + 3 * k];
+            if (dmo) dmo[r * Ds + d] += dm[k];
+            if (dvo) dvo[r * Ds + d] += dv[k];
+        }
+    }
+}
+
 extern "C" {
 
 int pilco_squash_sin(int U, int R, const double* m, const double* s, const double* max_action,
@@ -55,6 +73,15 @@ int pilco_exp_reward(int Ds, int R, const double* W, const double* t, const doub
     if (!W || !t || !m || !s || !muR) return PILCO_ERR_NULL;
     if (Ds < 1 || Ds > MAXD || R < 1) return PILCO_ERR_DIM;
     exp_reward_kernel<<<R, 128, 0, (cudaStream_t)stream>>>(Ds, W, t, m, s, muR, sR);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+int pilco_box_risk(int Ds, int R, const double* prm, const double* m, const double* s,
+                   double* risk, double* drisk_dm, double* drisk_dv, pilco_stream_t stream) {
+    if (!prm || !m || !s || !risk) return PILCO_ERR_NULL;
+    if (Ds < 1 || Ds > MAXD || R < 1) return PILCO_ERR_DIM;
+    box_risk_kernel<<<R, 32, 0, (cudaStream_t)stream>>>(Ds, prm, m, s, risk, drisk_dm, drisk_dv);
     CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }

@@ -18,6 +18,7 @@ struct RoDev {
     int n_rewards; pilco_reward_term rewards[8];
     const double* m0; long long m0_bs; const double* S0; long long S0_bs;
     double* traj_m; double* traj_S; double* reward; double* step_reward;
+    double* risk; double* step_risk; double mult_mu; int n_mult;     // MULT channel (SafePILCO): risk[t*R + r]
     // per-step slots [R, len] for step t (cur) and t-1 (prev)
     double *mj, *sj, *Mp, *Sp, *Vp, *Mu, *Su, *Cq, *Vu;
     double *mj_prev, *sj_prev, *Md_prev, *Sd_prev, *Vd_prev;
@@ -70,19 +71,30 @@ __global__ void __launch_bounds__(128) ro_state_kernel(RoDev p) {
                  p.Md_prev + (size_t)r * Ds, p.Sd_prev + (size_t)r * Ds * Ds, p.Vd_prev + (size_t)r * D * Ds,
                  mx, sx, sc);
     }
-    if (t >= p.H) return;
+    if (t >= p.H) {
+        // SafePILCO.predict (safe_pilco.py:49): reward_add + mu (1 - prod_t (1 - risk_t))
+        if (p.n_mult > 0 && tid == 0) {
+            double mult = 1.0;
+            for (int tt = 0; tt < p.H; ++tt) mult *= 1.0 - p.risk[(size_t)tt * p.R + r];
+            p.reward[r] += p.mult_mu * (1.0 - mult);
+        }
+        return;
+    }
     // expected reward at the pre-step state (pilco.py:130-134)
-    double rew = 0.0;
+    double rew = 0.0, risk = 0.0;
     for (int k = 0; k < p.n_rewards; ++k) {
         const pilco_reward_term& rt = p.rewards[k];
-        double mu;
-        if (rt.kind == PILCO_REWARD_EXP) mu = dev_exp_reward(Ds, rt.W, rt.t, mx, sx, nullptr, sc);
-        else mu = dev_linear_reward(Ds, rt.W, mx, sx, nullptr);
-        rew = fma(rt.coef, mu, rew);
+        const double mu = dev_reward_value(Ds, rt, mx, sx, sc);
+        if (rt.channel == PILCO_CHANNEL_MULT) risk = fma(rt.coef, mu, risk);
+        else rew = fma(rt.coef, mu, rew);
     }
     if (tid == 0) {
         p.reward[r] += rew;
         if (p.step_reward) p.step_reward[(size_t)r * p.H + t] = rew;
+        if (p.n_mult > 0) {
+            p.risk[(size_t)t * p.R + r] = risk;
+            if (p.step_risk) p.step_risk[(size_t)r * p.H + t] = risk;
+        }
     }
     if (p.pol_kind == PILCO_POLICY_LINEAR) {
         dev_linear_action(Ds, U, p.W + (size_t)r * p.W_bs, p.b + (size_t)r * p.b_bs, mx, sx,
@@ -118,8 +130,10 @@ int ro_check(const pilco_rollout* ro) {
     if (ro->n_rewards < 1 || ro->n_rewards > 8) return PILCO_ERR_DIM;
     for (int k = 0; k < ro->n_rewards; ++k) {
         if (!ro->rewards[k].W) return PILCO_ERR_NULL;
-        if (ro->rewards[k].kind == PILCO_REWARD_EXP && !ro->rewards[k].t) return PILCO_ERR_NULL;
-        if (ro->rewards[k].kind != PILCO_REWARD_EXP && ro->rewards[k].kind != PILCO_REWARD_LINEAR) return PILCO_ERR_UNSUPPORTED;
+        const int kind = ro->rewards[k].kind, ch = ro->rewards[k].channel;
+        if (kind == PILCO_REWARD_EXP && !ro->rewards[k].t) return PILCO_ERR_NULL;
+        if (kind != PILCO_REWARD_EXP && kind != PILCO_REWARD_LINEAR && kind != PILCO_REWARD_BOX) return PILCO_ERR_UNSUPPORTED;
+        if (ch != PILCO_CHANNEL_ADD && ch != PILCO_CHANNEL_MULT) return PILCO_ERR_UNSUPPORTED;
     }
     if (!ro->m0 || !ro->S0 || !ro->traj_m || !ro->traj_S || !ro->reward || !ro->ws) return PILCO_ERR_NULL;
     return PILCO_OK;
@@ -151,6 +165,7 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
     for (int k = 0; k < 8; ++k) d.rewards[k] = ro->rewards[k];
     d.m0 = ro->m0; d.m0_bs = ro->m0_bs; d.S0 = ro->S0; d.S0_bs = ro->S0_bs;
     d.traj_m = ro->traj_m; d.traj_S = ro->traj_S; d.reward = ro->reward; d.step_reward = ro->step_reward;
+    d.risk = ws + L.risk; d.step_risk = ro->step_risk; d.mult_mu = ro->mult_mu; d.n_mult = ro_count_mult(ro);
 
     auto slot = [&](size_t base, size_t len, int t) { return ws + base + (size_t)t * RR * len; };
     auto dyn_params = [&](int t) {

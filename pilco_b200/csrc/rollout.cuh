@@ -3,7 +3,7 @@
 #include "mm_kernels.cuh"
 
 struct RoWs {                 // offsets in doubles
-    size_t mj, sj, Md, Sd, Vd, Mp, Sp, Vp, Mu, Su, Cq, Vu, dynws, polws, total;
+    size_t mj, sj, Md, Sd, Vd, Mp, Sp, Vp, Mu, Su, Cq, Vu, risk, dynws, polws, total;
 };
 
 static inline RoWs ro_ws_layout(const pilco_rollout* ro) {
@@ -15,6 +15,7 @@ static inline RoWs ro_ws_layout(const pilco_rollout* ro) {
     L.Md = take(E); L.Sd = take(E * E); L.Vd = take(D * E);
     L.Mp = take(U); L.Sp = take(U * U); L.Vp = take(Ds * U);
     L.Mu = take(U); L.Su = take(U * U); L.Cq = take(U * U); L.Vu = take(Ds * U);
+    L.risk = take(1);                       // per-step risk of the MULT reward channel, [H][R]
     L.dynws = o; o += pilco_mm_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R) / 8;
     L.polws = o;
     if (ro->pol.kind == PILCO_POLICY_RBF)
@@ -24,3 +25,8 @@ static inline RoWs ro_ws_layout(const pilco_rollout* ro) {
 }
 
 int ro_check(const pilco_rollout* ro);
+static inline int ro_count_mult(const pilco_rollout* ro) {
+    int c = 0;
+    for (int k = 0; k < ro->n_rewards; ++k) c += ro->rewards[k].channel == PILCO_CHANNEL_MULT;
+    return c;
+}

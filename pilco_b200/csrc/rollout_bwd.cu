@@ -48,6 +48,7 @@ struct RbDev {
     const double* W; long long W_bs;
     int n_rewards; pilco_reward_term rewards[8];
     const double* traj_m; const double* traj_S;
+    const double* risk; double mult_mu;       // MULT channel: per-step risks risk[t*R + r] saved by the forward
     // forward slots of step t
     const double *sj, *Vd, *Mp, *Sp, *Vp, *Mu, *Su, *Cq, *Vu;
     // cotangent buffers [R, len]
@@ -146,10 +147,14 @@ __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
                        p.gW + (size_t)r * U * Ds, p.gb + (size_t)r * U, gm, gS, sc);
     }
     // ---- reward VJP at state t (pilco.py:133) ----
+    // MULT channel (safe_pilco.py:44-49): d[mu (1 - prod_t' (1 - risk_t'))] / d risk_t = mu prod_{t' != t} (1 - risk_t')
+    double wmult = p.mult_mu;
+    if (wmult != 0.0)
+        for (int tt = 0; tt < p.H; ++tt) if (tt != t) wmult *= 1.0 - p.risk[(size_t)tt * p.R + r];
     for (int k = 0; k < p.n_rewards; ++k) {
         const pilco_reward_term& rt = p.rewards[k];
-        if (rt.kind == PILCO_REWARD_EXP) dev_exp_reward_bwd(Ds, rt.W, rt.t, mx, sx, rt.coef, gm, gS, sc);
-        else { for (int i = tid; i < Ds; i += nt) gm[i] += rt.coef * rt.W[i]; __syncthreads(); }
+        const double scale = rt.channel == PILCO_CHANNEL_MULT ? rt.coef * wmult : rt.coef;
+        dev_reward_bwd(Ds, rt, mx, sx, scale, gm, gS, sc);
     }
 }
 
@@ -245,6 +250,7 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
     d.n_rewards = ro->n_rewards;
     for (int k = 0; k < 8; ++k) d.rewards[k] = ro->rewards[k];
     d.traj_m = ro->traj_m; d.traj_S = ro->traj_S;
+    d.risk = fws + FL.risk; d.mult_mu = ro_count_mult(ro) > 0 ? ro->mult_mu : 0.0;
     d.gm = buf(BL.gm); d.gS = buf(BL.gS); d.gMd = buf(BL.gMd); d.gSd = buf(BL.gSd); d.gVd = buf(BL.gVd);
     d.gmj = buf(BL.gmj); d.gsj = buf(BL.gsj); d.gsjx = buf(BL.gsjx);
     d.gMp = buf(BL.gMp); d.gSp = buf(BL.gSp); d.gVp = buf(BL.gVp);

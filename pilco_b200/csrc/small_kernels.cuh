@@ -4,6 +4,7 @@
 // Reference: pilco/controllers.py:13-58, pilco/rewards.py:19-61, pilco/models/pilco.py:138-153.
 #pragma once
 #include "common.cuh"
+#include "risk_math.cuh"
 
 #ifdef __CUDACC__
 
@@ -164,6 +165,14 @@ __device__ __forceinline__ double dev_linear_reward(int Ds, const double* W, con
     return mu;
 }
 
+// Expected value of one reward term at the state moments (m, s); every thread gets the value.
+__device__ __forceinline__ double dev_reward_value(int Ds, const pilco_reward_term& rt, const double* m, const double* s,
+                                                   SmallScratch& sc) {
+    if (rt.kind == PILCO_REWARD_EXP) return dev_exp_reward(Ds, rt.W, rt.t, m, s, nullptr, sc);
+    if (rt.kind == PILCO_REWARD_BOX) return risk_box_eval(Ds, rt.W, m, s, nullptr, nullptr);
+    return dev_linear_reward(Ds, rt.W, m, s, nullptr);
+}
+
 // ---------------------------------------------------------------------------------------------
 // VJPs (numpy statement: oracle/staged.py).  All "g*" outputs marked += accumulate.
 // ---------------------------------------------------------------------------------------------
@@ -286,6 +295,34 @@ __device__ __forceinline__ void dev_linear_bwd(int Ds, int U, const double* W, c
         gS[e] += v;
     }
     __syncthreads();
+}
+
+// Box-risk VJP (safe_pilco_extension/rewards_safe.py:13-58; formulas in risk_math.cuh):
+//   gm[d] += scale d risk/d m[d],  gS[d,d] += scale d risk/d s[d,d]   for the constrained dimensions
+__device__ __forceinline__ void dev_box_risk_bwd(int Ds, const double* prm, const double* m, const double* s,
+                                                 double scale, double* gm, double* gS) {
+    if (threadIdx.x == 0) {
+        double dm[RISK_MAX_DIMS], dv[RISK_MAX_DIMS];
+        risk_box_eval(Ds, prm, m, s, dm, dv);
+        const int nd = (int)prm[0];
+        for (int k = 0; k < nd; ++k) {
+            const int d = (int)prm[3 + 3 * k];
+            gm[d] += scale * dm[k];
+            gS[d * Ds + d] += scale * dv[k];
+        }
+    }
+    __syncthreads();
+}
+
+// VJP of one reward term with upstream weight `scale` (accumulates into gm, gS)
+__device__ __forceinline__ void dev_reward_bwd(int Ds, const pilco_reward_term& rt, const double* m, const double* s,
+                                               double scale, double* gm, double* gS, SmallScratch& sc) {
+    if (rt.kind == PILCO_REWARD_EXP) dev_exp_reward_bwd(Ds, rt.W, rt.t, m, s, scale, gm, gS, sc);
+    else if (rt.kind == PILCO_REWARD_BOX) dev_box_risk_bwd(Ds, rt.W, m, s, scale, gm, gS);
+    else {
+        for (int i = threadIdx.x; i < Ds; i += blockDim.x) gm[i] += scale * rt.W[i];
+        __syncthreads();
+    }
 }
 
 #endif  // __CUDACC__

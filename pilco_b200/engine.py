@@ -231,10 +231,27 @@ def exp_reward(W, t, m, s, variance=True):
     return mu, sR
 
 
-class RolloutPlan:
-    """Owns the buffers of one ``pilco_rollout`` description (batch R, horizon H) and launches it."""
+def box_risk(prm, m, s, grad=False):
+    """pilco_box_risk: prm = [nd, inside, sfac, (dim, low, high) x nd]; m [R,Ds], s [R,Ds,Ds] -> risk [R]
+    (+ d risk/d m [R,Ds], d risk/d diag(s) [R,Ds] when ``grad``)."""
+    prm, m, s = dev(prm), dev(m), dev(s)
+    R, Ds = m.shape
+    d = device()
+    risk = torch.empty(R, dtype=F64, device=d)
+    dm = torch.empty((R, Ds), dtype=F64, device=d) if grad else None
+    dv = torch.empty((R, Ds), dtype=F64, device=d) if grad else None
+    check(lib.pilco_box_risk(Ds, R, ptr(prm), ptr(m), ptr(s), ptr(risk), ptr(dm), ptr(dv), stream_ptr()), "box_risk")
+    return (risk, dm, dv) if grad else risk
 
-    def __init__(self, dyn, policy_spec, reward_terms, m0, S0, H, R=1):
+
+class RolloutPlan:
+    """Owns the buffers of one ``pilco_rollout`` description (batch R, horizon H) and launches it.
+
+    ``reward_terms``: dicts ``kind, coef, W, t`` (+ ``channel``: additive terms accumulate as in PILCO.predict,
+    pilco.py:130-134; multiplicative ones form the per-step risk of SafePILCO.predict, safe_pilco.py:29-50, and
+    enter the returned reward as ``mult_mu * (1 - prod_t (1 - risk_t))``)."""
+
+    def __init__(self, dyn, policy_spec, reward_terms, m0, S0, H, R=1, mult_mu=0.0):
         d = device()
         self.dyn = dyn
         self.R, self.H = int(R), int(H)
@@ -264,6 +281,7 @@ class RolloutPlan:
             W = dev(rt["W"]); t = dev(rt["t"]) if rt.get("t") is not None else None
             self.rw.append((W, t))
             ro.rewards[k].kind = rt["kind"]
+            ro.rewards[k].channel = int(rt.get("channel", _lib.CHANNEL_ADD))
             ro.rewards[k].coef = float(rt.get("coef", 1.0))
             ro.rewards[k].W = W.data_ptr()
             ro.rewards[k].t = t.data_ptr() if t is not None else None
@@ -277,6 +295,9 @@ class RolloutPlan:
         self.traj_S = torch.empty((self.R, self.H + 1, self.Ds, self.Ds), dtype=F64, device=d)
         self.reward = torch.empty(self.R, dtype=F64, device=d)
         self.step_reward = torch.empty((self.R, max(self.H, 1)), dtype=F64, device=d)
+        self.step_risk = torch.zeros((self.R, max(self.H, 1)), dtype=F64, device=d)
+        ro.mult_mu = float(mult_mu)
+        ro.step_risk = self.step_risk.data_ptr()
         self.info = torch.zeros(self.R, dtype=torch.int32, device=d)
         ro.traj_m, ro.traj_S = self.traj_m.data_ptr(), self.traj_S.data_ptr()
         ro.reward, ro.step_reward, ro.info = self.reward.data_ptr(), self.step_reward.data_ptr(), self.info.data_ptr()

@@ -62,11 +62,16 @@ class PILCO:
                         max_action=controllers._max_action_vec(c.max_action, U), gp=gp)
         raise TypeError("unsupported controller type %r" % type(c))
 
+    def reward_spec(self):
+        """(reward terms, mult_mu) handed to the device rollout; SafePILCO adds a multiplicative channel."""
+        return self.reward.terms(), 0.0
+
     def rollout_plan(self, m_x, s_x, n, flats=None):
         R = 1 if flats is None else int(np.asarray(flats).shape[0])
-        return engine.RolloutPlan(self.mgpr.device_gp(), self.policy_spec(flats), self.reward.terms(),
+        terms, mult_mu = self.reward_spec()
+        return engine.RolloutPlan(self.mgpr.device_gp(), self.policy_spec(flats), terms,
                                   np.asarray(m_x, dtype=np.float64).reshape(-1),
-                                  np.asarray(s_x, dtype=np.float64), int(n), R=R)
+                                  np.asarray(s_x, dtype=np.float64), int(n), R=R, mult_mu=mult_mu)
 
     def predict(self, m_x, s_x, n):
         """n-step cascade (pilco.py:118-136) -> (m [1,Ds], S [Ds,Ds], reward [1,1])."""

@@ -38,9 +38,11 @@ class PolicyEvaluator:
             spec = pilco.policy_spec(flat0)
             self.gp = spec["gp"]
         self.shape = (Ds, U)
-        self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, pilco.reward.terms(),
+        terms, mult_mu = pilco.reward_spec()
+        self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, terms,
                                        np.asarray(pilco.m_init, dtype=np.float64).reshape(-1),
-                                       np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=R)
+                                       np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=R,
+                                       mult_mu=mult_mu)
         self.h_flat = torch.empty((R, self.P), dtype=torch.float64).pin_memory()
         self.h_out = torch.empty((R, self.P + 2), dtype=torch.float64).pin_memory()
         self.d_flat = torch.empty((R, self.P), dtype=torch.float64, device=engine.device())

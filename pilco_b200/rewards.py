@@ -21,8 +21,8 @@ class ExponentialReward:
         mu, sR = engine.exp_reward(np.asarray(self.W), np.asarray(self.t).reshape(k), m, s, variance=True)
         return host(mu).reshape(1, 1), host(sR).reshape(1, 1)
 
-    def terms(self, coef=1.0):
-        return [dict(kind=_lib.REWARD_EXP, coef=float(coef), W=np.asarray(self.W),
+    def terms(self, coef=1.0, channel=_lib.CHANNEL_ADD):
+        return [dict(kind=_lib.REWARD_EXP, coef=float(coef), channel=channel, W=np.asarray(self.W),
                      t=np.asarray(self.t).reshape(self.state_dim))]
 
 
@@ -39,8 +39,9 @@ class LinearReward:
         s = np.asarray(s, dtype=np.float64).reshape(self.state_dim, self.state_dim)
         return m @ W, W.T @ s @ W
 
-    def terms(self, coef=1.0):
-        return [dict(kind=_lib.REWARD_LINEAR, coef=float(coef), W=np.asarray(self.W).reshape(self.state_dim), t=None)]
+    def terms(self, coef=1.0, channel=_lib.CHANNEL_ADD):
+        return [dict(kind=_lib.REWARD_LINEAR, coef=float(coef), channel=channel,
+                     W=np.asarray(self.W).reshape(self.state_dim), t=None)]
 
 
 class CombinedRewards:
@@ -59,8 +60,8 @@ class CombinedRewards:
             total_cov = total_cov + coef ** 2 * np.asarray(cov)
         return total_mean, total_cov
 
-    def terms(self, coef=1.0):
+    def terms(self, coef=1.0, channel=_lib.CHANNEL_ADD):
         out = []
         for reward, c in zip(self.base_rewards, np.asarray(self.coefs)):
-            out.extend(reward.terms(coef * float(c)))
+            out.extend(reward.terms(coef * float(c), channel))
         return out

@@ -22,18 +22,77 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), "libpilco_b200.so does not export %s" % name
     from pilco_b200 import _lib
     assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert _lib.lib.pilco_version() == 1
+    assert _lib.lib.pilco_version() == _lib.ABI_VERSION == 2
     assert _lib.lib.pilco_pad_n(300) == 320 and _lib.lib.pilco_pad_n(64) == 64
     assert _lib.lib.pilco_mm_workspace_bytes(300, 12, 10, 2) > 0
     assert _lib.lib.pilco_mm_workspace_bytes(300, 17, 10, 2) == 0          # D > PILCO_MAX_D rejected
     assert b"workspace" in _lib.lib.pilco_status_string(-3)
 
 
-def test_struct_layouts_match_header_sizes():
+def test_struct_layouts_match_header_sizes(tmp_path):
+    """Compile include/pilco_b200.h with the C compiler and compare every struct's size and field offsets with
+    the ctypes mirrors the Python host side passes through the ABI."""
+    import subprocess
     from pilco_b200 import _lib
+    exe = str(tmp_path / "abi_layout")
+    subprocess.check_call(["gcc", "-o", exe, os.path.join(ROOT, "tests", "host_harness", "abi_layout.c")])
+    mirror = {"pilco_gp_model": _lib.GpModel, "pilco_policy": _lib.Policy, "pilco_reward_term": _lib.RewardTerm,
+              "pilco_rollout": _lib.Rollout, "pilco_rollout_grad": _lib.RolloutGrad}
+    nchecked = 0
+    for line in subprocess.check_output([exe], text=True).splitlines():
+        parts = line.split()
+        kind, what, val = parts[0], parts[1] if len(parts) == 3 else "", parts[-1]
+        if kind == "sizeof":
+            assert ctypes.sizeof(mirror[what]) == int(val), what
+        elif kind == "offsetof":
+            st, field = what.split(".")
+            assert getattr(mirror[st], field).offset == int(val), what
+        else:
+            assert int(val) == _lib.ABI_VERSION
+        nchecked += 1
+    assert nchecked >= 40
     assert ctypes.sizeof(_lib.GpModel) == 4 * 4 + 4 * 16 + 16          # ints, 4x(ptr,stride), iK+ldk(+pad)
     assert ctypes.sizeof(_lib.RewardTerm) == 32
-    assert ctypes.sizeof(_lib.Rollout) % 8 == 0
+
+
+def test_box_risk_formulas_on_host(tmp_path):
+    """pilco_b200/csrc/risk_math.cuh (the code the device executes for the safe-PILCO risk rewards) compiled
+    for the host: value against the numpy restatement of rewards_safe.py, derivatives against torch autograd."""
+    import subprocess
+    from oracle import safe_port as sp
+    so = str(tmp_path / "risk_harness.so")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-o", so,
+                           os.path.join(ROOT, "tests", "host_harness", "risk_harness.cpp")])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.risk_box_eval_host.restype = ctypes.c_double
+    lib.risk_box_eval_host.argtypes = [ctypes.c_int, dp, dp, dp, dp, dp]
+    rng = np.random.RandomState(0)
+    Ds = 4
+    inf = float("inf")
+    cases = [((0, 2), (-0.3, -1.0), (0.4, 0.2), 2.0, True),         # RiskOfCollision
+             ((1,), (-0.2,), (inf,), 1.0, True),                      # SingleConstraint, low only
+             ((3,), (-inf,), (0.7,), 1.0, True),                      # high only
+             ((2,), (-0.5,), (0.6,), 1.0, False)]                     # both, complement
+    for dims, lows, highs, sfac, inside in cases:
+        m = rng.randn(1, Ds) * 0.3
+        a = rng.rand(Ds, Ds); s = 0.3 * a @ a.T + 0.2 * np.eye(Ds)
+        prm = np.array([len(dims), float(inside), sfac] + [v for k in range(len(dims)) for v in (dims[k], lows[k], highs[k])])
+        dm, dv = np.zeros(16), np.zeros(16)
+        c = lambda x: np.ascontiguousarray(x, dtype=np.float64).ctypes.data_as(dp)
+        val = lib.risk_box_eval_host(Ds, c(prm), c(m), c(s), dm.ctypes.data_as(dp), dv.ctypes.data_as(dp))
+        if len(dims) == 2:
+            ref = sp.risk_of_collision(m, s, lows, highs)[0]
+        else:
+            ref = sp.single_constraint(m, s, dims[0], high=None if highs[0] == inf else highs[0],
+                                       low=None if lows[0] == -inf else lows[0], inside=inside)[0]
+        assert abs(val - ref) < 1e-14
+        mt = torch.tensor(m, requires_grad=True); st = torch.tensor(s, requires_grad=True)
+        rt = sp.box_risk_torch(mt, st, dims, lows, highs, sfac, inside)
+        assert abs(float(rt.detach()) - val) < 1e-14
+        gm, gs = torch.autograd.grad(rt, [mt, st])
+        for k, d in enumerate(dims):
+            assert abs(dm[k] - float(gm[0, d])) < 1e-12 and abs(dv[k] - float(gs[d, d])) < 1e-12
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -149,3 +149,49 @@ def test_staged_closed_form_vjps():
     g = torch.autograd.grad((bt * T(gb)).sum(), [tX, tY, tl])
     gX, gY, gl = st.rbf_factor_backward(Xc, Yc, ell, gb)
     assert scaled_err(gX, g[0].numpy()) < 1e-10 and scaled_err(gY, g[1].numpy()) < 1e-10 and scaled_err(gl, g[2].numpy()) < 1e-10
+
+
+def test_safe_extension_ports_agree():
+    """oracle/safe_port.py: numpy transcription of safe_pilco_extension (SafePILCO.predict with a RiskOfCollision
+    multiplicative reward and an ObjectiveFunction additive reward) against its torch twin; the torch twin's
+    gradient against finite differences.  (No reference test exists for the extension: parity unpinned.)"""
+    import torch
+    from oracle import python_port as pp, torch_port as tp, safe_port as sp
+    from util import make_gp_problem
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    Ds, U, n, H, mu, mu_obj = 3, 1, 40, 4, 3.0, 0.7
+    X, Y, ell, sf2, sn2 = make_gp_problem(n, Ds + U, Ds, seed=2)
+    Y = 0.1 * Y
+    rng = np.random.RandomState(0)
+    W, b = rng.randn(U, Ds), rng.randn(1, U)
+    maxa = np.array([[1.3]])
+    Wr, tr = np.eye(Ds), 0.1 * np.ones((1, Ds))
+    low, high = np.array([0.1, -0.2]), np.array([0.9, 0.8])
+    m0, S0 = X[0:1, :Ds], 0.05 * np.eye(Ds)
+    iK, beta = pp.calculate_factorizations(X, Y, ell, sf2, sn2)
+    dyn = lambda m, s: pp.predict_given_factorizations(X, ell, sf2, m, s, iK, beta)
+    act = lambda m, s: pp.linear_action(W, b, m, s, True, maxa)
+    radd = sp.objective_function(lambda m, s: pp.exponential_reward(m, s, Wr, tr),
+                                 lambda m, s: sp.risk_of_collision(m, s, low, high), mu_obj)
+    rmult = lambda m, s: sp.single_constraint(m, s, 1, low=0.3)
+    Mn, Sn, tot = sp.safe_predict(m0, S0, H, lambda m, s: pp.propagate(m, s, act, dyn), radd, rmult, mu)
+
+    def torch_total(Wt):
+        iKt, bt = tp.calculate_factorizations(T(X), T(Y), T(ell), T(sf2), T(sn2))
+        dyn_t = lambda m, s: tp.predict_given_factorizations(T(X), T(ell), T(sf2), m, s, iKt, bt)
+        act_t = lambda m, s: tp.linear_action(Wt, T(b), m, s, T(maxa))
+        radd_t = lambda m, s: tp.exponential_reward(m, s, T(Wr), T(tr)) - mu_obj * sp.box_risk_torch(m, s, (0, 2), low, high, 2.0, True)
+        rmult_t = lambda m, s: sp.box_risk_torch(m, s, (1,), (0.3,), (float("inf"),), 1.0, True)
+        return sp.safe_predict_torch(T(m0), T(S0), H, lambda m, s: tp.propagate(m, s, act_t, dyn_t), radd_t, rmult_t, mu)
+
+    Wt = T(W).requires_grad_()
+    Mt, St, tt = torch_total(Wt)
+    assert abs(float(tot.item()) - float(tt.detach().item())) < 1e-10
+    assert np.max(np.abs(Mn - Mt.detach().numpy())) < 1e-10 and np.max(np.abs(Sn - St.detach().numpy())) < 1e-10
+    (gW,) = torch.autograd.grad(tt[0, 0], [Wt])
+    eps = 1e-6
+    for idx in [(0, 0), (0, 2)]:
+        Wp, Wm = W.copy(), W.copy()
+        Wp[idx] += eps; Wm[idx] -= eps
+        fd = (float(torch_total(T(Wp))[2].item()) - float(torch_total(T(Wm))[2].item())) / (2 * eps)
+        assert abs(fd - float(gW[idx])) < 1e-6 * max(1.0, abs(fd))
