@@ -67,6 +67,10 @@ class LinearController:
         return dict(kind=_lib.POLICY_LINEAR, Ds=Ds, U=U, squash=True, max_action=_max_action_vec(self.max_action, U),
                     W=W, b=b)
 
+    def state_key(self):
+        return hash((np.asarray(self.W).tobytes(), np.asarray(self.b).tobytes(),
+                     np.asarray(self.max_action, dtype=np.float64).tobytes()))
+
     def get_flat(self):
         return np.concatenate([np.asarray(self.W).ravel(), np.asarray(self.b).ravel()])
 
@@ -141,6 +145,9 @@ class RbfController(MGPR):
             m.Y.assign(self.max_action / 10 * np.random.normal(size=m.data[1].shape))
             mean, sigma = 1, 0.1
             m.kernel.lengthscales.assign(mean + sigma * np.random.normal(size=m.kernel.lengthscales.shape))
+
+    def state_key(self):
+        return hash((self._state_key(), np.asarray(self.max_action, dtype=np.float64).tobytes()))
 
     # ---- flat parameter vector: [centres (bf*Ds) | targets (bf*U) | unconstrained lengthscales (U*Ds)] ----
     @property

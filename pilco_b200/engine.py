@@ -408,3 +408,77 @@ class SplitRollout:
     @property
     def info(self):
         return torch.cat([p.info for p in self.plans])
+
+
+class ActionPlan:
+    """Low-latency policy evaluation at a deterministic state: u = E[pi(x)] with s = 0, the call
+    ``PILCO.compute_action`` makes once per control step when a learnt policy drives the plant
+    (pilco/models/pilco.py:115-116, examples/utils.py:32-36).
+
+    All buffers are allocated once; host->device copy of the state, the policy moment match
+    (``pilco_mm_forward`` in deterministic-GP mode or ``pilco_linear_action``), ``pilco_squash_sin`` and the
+    device->host copy of the action are captured in ONE CUDA graph, so a control step costs one graph launch and
+    one stream synchronisation instead of ~10 allocations and 4-6 separate launches."""
+
+    def __init__(self, policy_spec):
+        d = device()
+        self.Ds, self.U = int(policy_spec["Ds"]), int(policy_spec["U"])
+        Ds, U = self.Ds, self.U
+        self.kind = policy_spec["kind"]
+        self.squash = bool(policy_spec.get("squash", True))
+        self.h_x = torch.zeros((1, Ds), dtype=F64).pin_memory()
+        self.h_out = torch.zeros((1, U + 1), dtype=F64).pin_memory()          # [action | info]
+        self.m = torch.zeros((1, Ds), dtype=F64, device=d)
+        self.s = torch.zeros((1, Ds, Ds), dtype=F64, device=d)
+        self.M = torch.empty((1, U), dtype=F64, device=d)
+        self.S = torch.empty((1, U, U), dtype=F64, device=d)
+        self.V = torch.empty((1, Ds, U), dtype=F64, device=d)
+        self.Mu = torch.empty((1, U), dtype=F64, device=d)
+        self.Su = torch.empty((1, U, U), dtype=F64, device=d)
+        self.Cq = torch.empty((1, U, U), dtype=F64, device=d)
+        self.out = torch.zeros((1, U + 1), dtype=F64, device=d)
+        self.info = torch.zeros(1, dtype=torch.int32, device=d)
+        self.maxa = dev(np.broadcast_to(np.asarray(policy_spec.get("max_action", 1.0), dtype=np.float64).ravel(),
+                                        (U,)).copy())
+        if self.kind == _lib.POLICY_LINEAR:
+            self.W, self.b = dev(policy_spec["W"]).reshape(U, Ds), dev(policy_spec["b"]).reshape(U)
+        else:
+            self.gp = policy_spec["gp"]
+            if self.gp.batched:
+                raise ValueError("ActionPlan evaluates ONE policy (unbatched parameters)")
+            self.gps = self.gp.struct()
+            self.wsb = lib.pilco_mm_workspace_bytes(self.gp.n, self.gp.D, self.gp.E, 1)
+            self.ws = torch.empty(self.wsb // 8, dtype=F64, device=d)
+        self._enqueue()                                    # eager warm-up (one-time kernel attributes)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+
+    def _enqueue(self):
+        U = self.U
+        self.m.copy_(self.h_x, non_blocking=True)
+        if self.kind == _lib.POLICY_LINEAR:
+            check(lib.pilco_linear_action(self.Ds, U, 1, ptr(self.W), 0, ptr(self.b), 0, ptr(self.m), ptr(self.s),
+                                          ptr(self.M), ptr(self.S), ptr(self.V), stream_ptr()), "linear_action")
+        else:
+            check(lib.pilco_mm_forward(C.byref(self.gps), 1, ptr(self.m), ptr(self.s), ptr(self.M), ptr(self.S),
+                                       ptr(self.V), ptr(self.info), ptr(self.ws), self.wsb, stream_ptr()), "mm_forward")
+        if self.squash:
+            check(lib.pilco_squash_sin(U, 1, ptr(self.M), ptr(self.S), ptr(self.maxa), ptr(self.Mu), ptr(self.Su),
+                                       ptr(self.Cq), stream_ptr()), "squash_sin")
+            self.out[:, :U] = self.Mu
+        else:
+            self.out[:, :U] = self.M
+        self.out[:, U] = self.info.to(F64)
+        self.h_out.copy_(self.out, non_blocking=True)
+
+    def __call__(self, x):
+        """x [Ds] or [1,Ds] (host) -> action [1,U] (host ndarray)"""
+        self.h_x.copy_(torch.as_tensor(np.asarray(x, dtype=np.float64).reshape(1, self.Ds)))
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        res = self.h_out.numpy()
+        if res[0, self.U] != 0.0:
+            raise RuntimeError("policy moment match failed (info=%d)" % int(res[0, self.U]))
+        return res[:, :self.U].copy()

@@ -97,7 +97,15 @@ class PILCO:
         return -self.training_loss()
 
     def compute_action(self, x_m):
-        return self.controller.compute_action(x_m, np.zeros([self.state_dim, self.state_dim]))[0]
+        """pilco.py:115-116: the policy mean at a deterministic state (s = 0).  Served by a cached
+        ``engine.ActionPlan`` (one captured CUDA graph per policy state) -- the per-control-step call of
+        examples/utils.py:32-36."""
+        from ..params import HostArray
+        key = self.controller.state_key()
+        if key != getattr(self, "_act_key", None):
+            self._act_plan = engine.ActionPlan(self.policy_spec())
+            self._act_key = key
+        return self._act_plan(x_m).view(HostArray)
 
     # ---- model training (pilco.py:52-73) ------------------------------------------------------------
     def optimize_models(self, maxiter=200, restarts=1):
