@@ -373,7 +373,7 @@ def run_ours(args):
                 "frac": alg_bytes / (tile_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
     }
-    cpu_v, cores, sample = cpu_reference_steps_per_s(wl, reps=2, h_sample=4)
+    cpu_v, cores, sample = cpu_reference_steps_per_s(wl, reps=2, h_sample=4) if args.cpu_baseline else (None, 0, "skipped (--no-cpu-baseline)")
     launches_per_step = nsplit * ((H * 8 + 1) + 1)                  # per sub-batch: ro_state + policy(setup1,setup2,tile,ro_policy) + dyn(setup1,setup2,tile); +memset
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -404,6 +404,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--restarts", type=int, default=32, help="policy restarts per GPU")
     ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward extra line")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="tuning runs: skip the CPU leg")
     ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpilco_b200.so")
+LIB_PATH = os.environ.get("PILCO_B200_LIB") or os.path.join(_HERE, "libpilco_b200.so")   # env: diagnostics builds
 
 c_dp = C.c_void_p          # device pointers are passed as integers (tensor.data_ptr())
 c_ll = C.c_longlong

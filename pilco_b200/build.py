@@ -32,12 +32,14 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra_flags=(), lib=None, build_dir=None):
+    """``extra_flags``/``lib``/``build_dir``: diagnostics variants (e.g. -DPILCO_TILE_TIMING) built beside the product
+    library; the default call builds ``libpilco_b200.so``."""
+    if lib is None and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = build_dir or os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -46,7 +48,7 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, pr in procs:
         out, _ = pr.communicate()
@@ -54,12 +56,17 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
         if verbose and out:
             sys.stderr.write(out)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    out_lib = lib or LIB
+    cmd = [nvcc, "-shared", "-o", out_lib] + objs + ["-lcudart"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)
-    return LIB
+    return out_lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timing" in sys.argv:      # diagnostics variant with per-CTA phase stamps in the tile kernel
+        print(build(force=True, extra_flags=["-DPILCO_TILE_TIMING"], lib=os.path.join(HERE, "build_timing", "libpilco_b200_timing.so"),
+                    build_dir=os.path.join(HERE, "build_timing")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -254,7 +254,8 @@ __device__ __forceinline__ double exp_shifted(double c, double am, const double*
 __device__ __forceinline__ void exp_row_split(double A, double& am, double& rowfac) {
     const double Ai = rint(A);
     am = EXP_MAGIC + Ai;
-    rowfac = exp((A - Ai) * (1.0 / EXP_SC));
+    const double y = (A - Ai) * (1.0 / EXP_SC);           // |y| <= 0.5/EXP_SC = 3.4e-4: degree-4 Taylor, error < 4e-20
+    rowfac = fma(y, fma(y, fma(y, fma(y, 1.0 / 24.0, 1.0 / 6.0), 0.5), 1.0), 1.0);
 }
 
 // ---------------------------------------------------------------------------------------------

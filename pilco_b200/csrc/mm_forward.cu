@@ -17,9 +17,12 @@ template <int KS>
 static int launch_tile(const MMParams& p, cudaStream_t st) {
     static bool configured = false;
     static int variant = 1;          // 0: 2 CTAs/SM (<=128 regs), 1: 3 CTAs/SM (<=85 regs)
+    static int rpc_env = 0;          // 0: automatic
     if (!configured) {
-        const char* e = getenv("PILCO_TILE_VARIANT");       // tuning switch
+        const char* e = getenv("PILCO_TILE_VARIANT");       // tuning switches
         if (e && e[0] >= '0' && e[0] <= '2') variant = e[0] - '0';
+        const char* e2 = getenv("PILCO_TILE_RPC");
+        if (e2) rpc_env = atoi(e2);
         const int big = (int)mm_tile_smem_bytes(TILE_CM, 20);
         if (cudaFuncSetAttribute(mm_tile_kernel<KS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         if (cudaFuncSetAttribute(mm_tile_kernel<KS, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
@@ -29,10 +32,19 @@ static int launch_tile(const MMParams& p, cudaStream_t st) {
     int rc = exp_table_upload();
     if (rc) return rc;
     const size_t smem = mm_tile_smem_bytes(p.L.np, p.L.ldz);
-    dim3 grid(p.L.NB, p.L.P, p.R);
-    if (variant == 2) mm_tile_kernel<KS, 4><<<grid, 256, smem, st>>>(p);
-    else if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p);
-    else mm_tile_kernel<KS, 2><<<grid, 256, smem, st>>>(p);
+    // row blocks per CTA: a CTA's fixed cost (TMA staging of the columns and the exp table, barrier, first-load
+    // latency: ~5 k cycles against ~16 k per 64-row sweep at the metric shape) is paid once for all its row blocks.
+    // All of a pair's row blocks go to one CTA as soon as pairs x restarts still give every SM a CTA; smaller
+    // launches keep enough CTAs to fill the machine (2 x 148).
+    int rpc = p.L.NB;
+    const long long pr = (long long)p.L.P * p.R;
+    if (pr < 148) { rpc = (int)(((long long)p.L.NB * pr) / 296); if (rpc < 1) rpc = 1; }
+    if (rpc_env > 0) rpc = rpc_env;
+    if (rpc > p.L.NB) rpc = p.L.NB;
+    dim3 grid((p.L.NB + rpc - 1) / rpc, p.L.P, p.R);
+    if (variant == 2) mm_tile_kernel<KS, 4><<<grid, 256, smem, st>>>(p, rpc);
+    else if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p, rpc);
+    else mm_tile_kernel<KS, 2><<<grid, 256, smem, st>>>(p, rpc);
     return PILCO_OK;
 }
 
@@ -130,3 +142,9 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
 }
 
 }  // extern "C"
+
+#ifdef PILCO_TILE_TIMING
+extern "C" int pilco_debug_tile_timing(long long* host_out, int n) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_tile_timing, sizeof(long long) * (size_t)n);
+}
+#endif

@@ -23,7 +23,7 @@
 #define PAIR_BLK (2 * MAXD * MAXD + 2 * MAXD + 8)
 
 struct MMWs {            // workspace layout, offsets in doubles relative to the per-restart base
-    size_t zeta, betap, Bq, Tpart, Wm, Wc, Qab, per_r;
+    size_t zeta, betap, Bq, Tpart, Wm, Wc, Qab, Ufrag, Arow, per_r;
     int np, ldz, P, NB;
 };
 
@@ -39,6 +39,12 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     L.Wm = o;    o += (size_t)E * MAXD * MAXD;          // setup stage 1 -> 2: W_a
     L.Wc = o;    o += (size_t)((E + 1) & ~1);           //                      c_a
     L.Qab = o;   o += (size_t)L.P * PAIR_BLK;           //                      per-pair block (see PAIR_*)
+    o = (o + 1) & ~(size_t)1;
+    // forward (unordered pairs): row-side operands of every (pair, row octet) materialised by setup stage 2 so that
+    // the tile CTAs start their column sweep after one round of loads -- U' as DMMA A fragments
+    // [P][np/8][KS][32 lanes] and the scalar A'[P][np].  The backward tile kernel derives them in its prologue.
+    L.Ufrag = o; if (!ordered) o += (size_t)L.P * (L.np / 8) * ksteps_of(D) * 32;
+    L.Arow = o;  if (!ordered) o += (size_t)L.P * L.np;
     L.per_r = (o + 1) & ~(size_t)1;
     return L;
 }
@@ -248,6 +254,11 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p)
     }
 }
 
+template <int KS> struct RowOpConsts;
+template <int KS>
+__device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, const double* __restrict__ zr,
+                                                     bool live, int lane, double (&ua)[KS], double& Apv);
+
 // stage 2: the throughput part: one CTA (128 threads) per task sweeps the centres
 template <int DP, bool BWD>
 __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
@@ -358,6 +369,8 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
             bqb[ks][nt] = i < DP ? sQb[i * DP + 4 * ks + t] : 0.0;
         }
     const double lsb = blk[PAIR_SC + 2];
+    RowOpConsts<KS> roc;                                        // row-side pair constants, loaded once per CTA
+    if (!BWD) roc.load(blk, lane);
     for (int n0 = 0; n0 < np; n0 += 128) {
         // stage zeta[n0 : n0+128, 0:ldz] = X - m (zero outside [n, D)) in shared memory, coalesced
         __syncthreads();
@@ -401,39 +414,72 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
             kbp += __shfl_xor_sync(0xffffffffu, kbp, 1); kbp += __shfl_xor_sync(0xffffffffu, kbp, 2);
             qbp += __shfl_xor_sync(0xffffffffu, qbp, 1); qbp += __shfl_xor_sync(0xffffffffu, qbp, 2);
             if (t == 0) wsr[L.Bq + (size_t)q * np + row] = row < n ? EXP_SC * (lsb - 0.5 * kbp + qbp) : NEG_PAD;
+            if (!BWD) {
+                // row side of the same 8 centres: DMMA A fragments of U' and the scalar A' (see tile_row_operands),
+                // written in the layout the tile kernel's prologue loads with three coalesced 8-byte loads per lane
+                double ua[KS], Apv;
+                row_operands_compute<KS>(roc, zr, row < n, lane, ua, Apv);
+                double* uf = wsr + L.Ufrag + ((size_t)q * (np >> 3) + ((n0 >> 3) + grp)) * (KS * 32);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) uf[ks * 32 + lane] = ua[ks];
+                if (t == 0) wsr[L.Arow + (size_t)q * np + row] = Apv;
+            }
         }
     }
 }
 
 // Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
 // U' = 2 EXP_SC p_b o (Qa zeta_row), and the scalar A'[row] = EXP_SC (log sf2_a - 0.5 sum p_a zeta^2 + z_a'Q z_a
-// - 0.5 log det R).  zeta rows are read from the workspace (L2 resident); 2*ceil(DP/8)*KS DMMA + 2 KS shuffles.
+// - 0.5 log det R).  2*ceil(DP/8)*KS DMMA + 2 KS shuffles per 8 rows.  The pair constants (this lane's B fragments
+// of Qa and its slices of p_a, p_b) are loaded once (RowOpConsts) and reused for every row octet.
 template <int KS>
-__device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk, const double* __restrict__ zeta,
-                                                  int ldz, int row, bool live, int lane,
-                                                  double (&ua)[KS], double& Apv) {
+struct RowOpConsts {
+    static constexpr int DP = 4 * KS, NT = (DP + 7) / 8;
+    double bq[KS][NT];          // B fragments: Qa[8 nt + g][4 ks + t]
+    double pak[KS];             // p_a[4 ks + t]
+    double pac[NT][2], pbc[NT][2];   // p_a, p_b at this lane's C-fragment columns 8 nt + 2 t (+1)
+    double lsa, hld;            // log sf2_a, 0.5 log det R
+    __device__ __forceinline__ void load(const double* __restrict__ blk, int lane) {
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            pak[ks] = blk[PAIR_PA + 4 * ks + t];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int i = 8 * nt + g;
+                bq[ks][nt] = i < DP ? blk[PAIR_QA + i * DP + 4 * ks + t] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int i0 = 8 * nt + 2 * t;
+            const bool in = i0 < DP;
+            pac[nt][0] = in ? blk[PAIR_PA + i0] : 0.0; pac[nt][1] = in ? blk[PAIR_PA + i0 + 1] : 0.0;
+            pbc[nt][0] = in ? blk[PAIR_PB + i0] : 0.0; pbc[nt][1] = in ? blk[PAIR_PB + i0 + 1] : 0.0;
+        }
+        lsa = blk[PAIR_SC + 1]; hld = blk[PAIR_SC + 0];
+    }
+};
+
+// zr = zeta row of this lane's centre (row g of the octet), readable at [0, ldz)
+template <int KS>
+__device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, const double* __restrict__ zr,
+                                                     bool live, int lane, double (&ua)[KS], double& Apv) {
     constexpr int DP = 4 * KS, NT = (DP + 7) / 8;
-    const int g = lane >> 2, t = lane & 3;
-    const double* zr = zeta + (size_t)row * ldz;
-    const double* pa = blk + PAIR_PA;
-    const double* pb = blk + PAIR_PB;
+    const int t = lane & 3;
     double z[KS], va[NT][2];
     double kap = 0.0;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         z[ks] = zr[4 * ks + t];
-        kap = fma(pa[4 * ks + t] * z[ks], z[ks], kap);
+        kap = fma(c.pak[ks] * z[ks], z[ks], kap);
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { va[nt][0] = va[nt][1] = 0.0; }
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int i = 8 * nt + g;
-            const double bq = i < DP ? blk[PAIR_QA + i * DP + 4 * ks + t] : 0.0;
-            dmma884(va[nt][0], va[nt][1], z[ks], bq);
-        }
+        for (int nt = 0; nt < NT; ++nt) dmma884(va[nt][0], va[nt][1], z[ks], c.bq[ks][nt]);
     double qap = 0.0;
     double uc[NT][2];
 #pragma unroll
@@ -441,14 +487,14 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
         const int i0 = 8 * nt + 2 * t;
         uc[nt][0] = uc[nt][1] = 0.0;
         if (i0 < DP) {
-            qap = fma(pa[i0] * zr[i0], va[nt][0], fma(pa[i0 + 1] * zr[i0 + 1], va[nt][1], qap));
-            uc[nt][0] = (2.0 * EXP_SC) * pb[i0] * va[nt][0];
-            uc[nt][1] = (2.0 * EXP_SC) * pb[i0 + 1] * va[nt][1];
+            qap = fma(c.pac[nt][0] * zr[i0], va[nt][0], fma(c.pac[nt][1] * zr[i0 + 1], va[nt][1], qap));
+            uc[nt][0] = (2.0 * EXP_SC) * c.pbc[nt][0] * va[nt][0];
+            uc[nt][1] = (2.0 * EXP_SC) * c.pbc[nt][1] * va[nt][1];
         }
     }
     kap += __shfl_xor_sync(0xffffffffu, kap, 1); kap += __shfl_xor_sync(0xffffffffu, kap, 2);
     qap += __shfl_xor_sync(0xffffffffu, qap, 1); qap += __shfl_xor_sync(0xffffffffu, qap, 2);
-    Apv = live ? EXP_SC * (blk[PAIR_SC + 1] - 0.5 * kap + qap - blk[PAIR_SC + 0]) : NEG_PAD;
+    Apv = live ? EXP_SC * (c.lsa - 0.5 * kap + qap - c.hld) : NEG_PAD;
     // C-fragment layout (row g, cols 8nt+2t,+1) -> A-fragment layout (row g, col 4ks+t)
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -458,6 +504,16 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
         const double x1 = __shfl_sync(0xffffffffu, uc[nt][1], src);
         ua[ks] = (t & 1) ? x1 : x0;
     }
+}
+
+// one-shot form (backward tile kernel prologue): zeta rows are read from the workspace (L2 resident)
+template <int KS>
+__device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk, const double* __restrict__ zeta,
+                                                  int ldz, int row, bool live, int lane,
+                                                  double (&ua)[KS], double& Apv) {
+    RowOpConsts<KS> c;
+    c.load(blk, lane);
+    row_operands_compute<KS>(c, zeta + (size_t)row * ldz, live, lane, ua, Apv);
 }
 
 // both stages
@@ -483,9 +539,20 @@ static inline __host__ __device__ int mm_tile_slots(int np) { return np / 8; }
 
 // Body of one tile CTA, specialised on the pair kind so that off-diagonal pairs carry neither the
 // triangle bookkeeping nor the (predicated-off but still issued) trace FMAs of the diagonal pairs.
+#ifdef PILCO_TILE_TIMING
+// diagnostics build only (scripts/tile_phases.py): per CTA, warp 0 records clock64() at entry, after the row
+// operands, after the first TMA wait, after the column sweep and at exit.
+__device__ long long g_tile_timing[5 * 16384];
+#define TILE_STAMP(k) do { if (threadIdx.x == 0) { const unsigned c_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+                                                   if (c_ < 16384) g_tile_timing[5 * c_ + (k)] = clock64(); } } while (0)
+#else
+#define TILE_STAMP(k) do { } while (0)
+#endif
+
 template <int KS, bool SYM, bool DIAG>
-__device__ __forceinline__ void mm_tile_body(const MMParams& p) {
+__device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    TILE_STAMP(0);
     const MMWs& L = p.L;
     constexpr int ldz = KS == 1 ? 4 : (KS <= 3 ? 12 : 20);    // == ldz_of(D) for every D with ksteps_of(D) == KS
     const int np = L.np, n = p.gp.n;
@@ -496,25 +563,26 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
     double* tab = sBe + CM;
     uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
 
-    const int r = blockIdx.z, q = blockIdx.y, rb = blockIdx.x;
+    // this CTA: pair q of restart r, row blocks [rb0, rb1) swept one after the other (the staged columns, the exp
+    // table and the barrier are set up once per CTA; only the row operands change between passes)
+    const int r = blockIdx.z, q = blockIdx.y;
+    const int rb0 = blockIdx.x * rpc;
+    const int rb1 = (rb0 + rpc) < L.NB ? (rb0 + rpc) : L.NB;
     int a, b;
     pair_decode(q, a, b);
     const double* wsr = p.ws + (size_t)r * L.per_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int row0 = rb * 64 + warp * 8;
-    const int row = row0 + g;
-    const bool active = row0 < n;                      // warp-uniform
     const int ncol8 = (n + 7) & ~7;                    // columns at or beyond this are pure padding
     constexpr bool sympair = SYM;                      // symmetric pair (a == b): visit the upper triangle only
     constexpr bool diag = DIAG;                        // ... and (exact-GP mode) subtract the trace term
-    // first column this CTA needs (symmetric pairs skip everything left of its first row tile)
-    const int cfirst = sympair ? rb * 64 : 0;
+    const bool single = ncol8 <= CM;                   // one chunk holds every column: staged once for all passes
 
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
 
-    // stage one column chunk (zeta rows, B_q, beta_b) and, with the first chunk, the exp table
-    auto issue_chunk = [&](int c0, bool with_table) {
+    // stage one column chunk (zeta rows, B_q, beta_b) and, with the first chunk, the exp table; symmetric pairs
+    // skip everything left of the row tile `cfirst`
+    auto issue_chunk = [&](int c0, int cfirst, bool with_table) {
         const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
         const int cm = (np - c0) < CM ? (np - c0) : CM;
         const int ncopy = cm - lo;
@@ -525,114 +593,141 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p) {
         tma_bulk_g2s(sBe + lo, wsr + L.betap + (size_t)b * np + c0 + lo, (unsigned)(ncopy * 8), bar);
         if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
     };
-    const int cbeg = (cfirst / CM) * CM;
-    if (tid == 0 && cbeg < ncol8) issue_chunk(cbeg, true);
-    // row operands are computed while the copies are in flight
-    double ua[KS], Apv;
-    tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < n, lane, ua, Apv);
-    // integer part of A' rides in the rounding constant of the exp, the fractional part scales the row sums
-    double am, rowfac;
-    exp_row_split(Apv, am, rowfac);
-    const double ba = wsr[L.betap + (size_t)a * np + row] * rowfac;
-    const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+    {
+        const int cfirst0 = sympair ? rb0 * 64 : 0;
+        const int cbeg0 = (cfirst0 / CM) * CM;
+        if (tid == 0 && cbeg0 < ncol8) issue_chunk(cbeg0, cfirst0, true);
+    }
+    TILE_STAMP(1);
     __syncthreads();                                    // barrier initialisation visible to the waiting warps
 
-    double acc2 = 0.0, accd = 0.0, tr2 = 0.0, trd = 0.0;   // strictly-upper / diagonal-tile accumulators
     unsigned phase = 0;
-    for (int c0 = cbeg; c0 < ncol8; c0 += CM) {
-        const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
-        const int cm = (np - c0) < CM ? (np - c0) : CM;
-        const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;        // chunk-local end of valid columns
-        if (c0 != cbeg) {
-            __syncthreads();                                           // all warps done with the previous chunk
-            if (tid == 0) issue_chunk(c0, false);
+    bool staged = true;                                 // the chunk issued at entry has not been consumed yet
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const int row0 = rb * 64 + warp * 8;
+        const int row = row0 + g;
+        const bool active = row0 < n;                  // warp-uniform
+        // row operands (materialised by setup stage 2): DMMA A fragments of U' and the scalar A'
+        double ua[KS], Apv;
+        {
+            const double* uf = wsr + L.Ufrag + ((size_t)q * (np >> 3) + (row0 >> 3)) * (KS * 32);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) ua[ks] = uf[ks * 32 + lane];
+            Apv = wsr[L.Arow + (size_t)q * np + row];
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        if (active) {
-            // symmetric pairs start at this warp's own row tile (global column row0)
-            int cstart = lo;
-            if (sympair && row0 > c0 + lo) cstart = (row0 - c0) & ~31;
-            if (cstart < lo) cstart = lo;
-            for (int cg = cstart; cg < cend; cg += 32) {
-                double2 ik[4];
-                if (diag) {
+        // integer part of A' rides in the rounding constant of the exp, the fractional part scales the row sums
+        double am, rowfac;
+        exp_row_split(Apv, am, rowfac);
+        const double ba = wsr[L.betap + (size_t)a * np + row] * rowfac;
+        const double* ikrow = diag ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+        // first column this pass needs (symmetric pairs skip everything left of its row tile)
+        const int cfirst = sympair ? rb * 64 : 0;
+        const int cbeg = (cfirst / CM) * CM;
+
+        double acc2 = 0.0, accd = 0.0, tr2 = 0.0, trd = 0.0;   // strictly-upper / diagonal-tile accumulators
+        for (int c0 = cbeg; c0 < ncol8; c0 += CM) {
+            const int lo = cfirst > c0 ? cfirst - c0 : 0;                  // chunk-local first column (multiple of 64)
+            const int cm = (np - c0) < CM ? (np - c0) : CM;
+            const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;        // chunk-local end of valid columns
+            if (staged) {                                                  // chunk issued at CTA entry
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                staged = false;
+                TILE_STAMP(2);
+            } else if (!single) {
+                __syncthreads();                                           // all warps done with the previous chunk
+                if (tid == 0) issue_chunk(c0, cfirst, false);
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            if (active) {
+                // symmetric pairs start at this warp's own row tile (global column row0)
+                int cstart = lo;
+                if (sympair && row0 > c0 + lo) cstart = (row0 - c0) & ~31;
+                if (cstart < lo) cstart = lo;
+                for (int cg = cstart; cg < cend; cg += 32) {
+                    double2 ik[4];
+                    if (diag) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        ik[j] = *reinterpret_cast<const double2*>(ikrow + c0 + cg + 8 * j + 2 * t);   // zero padded: always in bounds
-                }
-                // fast path: all four tiles valid and (symmetric pairs) strictly right of the diagonal tile
-                const bool full = (cg + 32 <= cend) && (!sympair || c0 + cg > row0);
-                if (full) {
-                    double e[8];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double2 bq = *reinterpret_cast<const double2*>(sBq + cg + 8 * j + 2 * t);
-                        e[2 * j] = bq.x; e[2 * j + 1] = bq.y;
+                        for (int j = 0; j < 4; ++j)
+                            ik[j] = *reinterpret_cast<const double2*>(ikrow + c0 + cg + 8 * j + 2 * t);   // zero padded: always in bounds
                     }
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
+                    // fast path: all four tiles valid and (symmetric pairs) strictly right of the diagonal tile
+                    const bool full = (cg + 32 <= cend) && (!sympair || c0 + cg > row0);
+                    if (full) {
+                        double e[8];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const double bf = sZ[(size_t)(cg + 8 * j + g) * ldz + 4 * ks + t];
-                            dmma884(e[2 * j], e[2 * j + 1], ua[ks], bf);
+                            const double2 bq = *reinterpret_cast<const double2*>(sBq + cg + 8 * j + 2 * t);
+                            e[2 * j] = bq.x; e[2 * j + 1] = bq.y;
                         }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double l0 = exp_shifted(e[2 * j], am, tab), l1 = exp_shifted(e[2 * j + 1], am, tab);
-                        const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
-                        acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
-                        if (diag) { tr2 = fma(ik[j].x, l0, tr2); tr2 = fma(ik[j].y, l1, tr2); }
-                    }
-                    continue;
-                }
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const int col = cg + 8 * j;
-                    const int gcol = c0 + col;
-                    if (col < cend && (!sympair || gcol >= row0)) {         // warp-uniform
-                        const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
-                        double e0 = bq.x, e1 = bq.y;
 #pragma unroll
                         for (int ks = 0; ks < KS; ++ks) {
-                            const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
-                            dmma884(e0, e1, ua[ks], bf);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const double bf = sZ[(size_t)(cg + 8 * j + g) * ldz + 4 * ks + t];
+                                dmma884(e[2 * j], e[2 * j + 1], ua[ks], bf);
+                            }
                         }
-                        const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
-                        const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
-                        const double2 ikj = diag ? *reinterpret_cast<const double2*>(ikrow + gcol + 2 * t) : make_double2(0.0, 0.0);
-                        if (sympair && gcol == row0) {
-                            accd = fma(bb.x, l0, accd); accd = fma(bb.y, l1, accd);
-                            trd = fma(ikj.x, l0, trd); trd = fma(ikj.y, l1, trd);
-                        } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double l0 = exp_shifted(e[2 * j], am, tab), l1 = exp_shifted(e[2 * j + 1], am, tab);
+                            const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
                             acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
-                            tr2 = fma(ikj.x, l0, tr2); tr2 = fma(ikj.y, l1, tr2);
+                            if (diag) { tr2 = fma(ik[j].x, l0, tr2); tr2 = fma(ik[j].y, l1, tr2); }
+                        }
+                        continue;
+                    }
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        const int col = cg + 8 * j;
+                        const int gcol = c0 + col;
+                        if (col < cend && (!sympair || gcol >= row0)) {         // warp-uniform
+                            const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
+                            double e0 = bq.x, e1 = bq.y;
+#pragma unroll
+                            for (int ks = 0; ks < KS; ++ks) {
+                                const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
+                                dmma884(e0, e1, ua[ks], bf);
+                            }
+                            const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
+                            const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
+                            const double2 ikj = diag ? *reinterpret_cast<const double2*>(ikrow + gcol + 2 * t) : make_double2(0.0, 0.0);
+                            if (sympair && gcol == row0) {
+                                accd = fma(bb.x, l0, accd); accd = fma(bb.y, l1, accd);
+                                trd = fma(ikj.x, l0, trd); trd = fma(ikj.y, l1, trd);
+                            } else {
+                                acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
+                                tr2 = fma(ikj.x, l0, tr2); tr2 = fma(ikj.y, l1, tr2);
+                            }
                         }
                     }
                 }
             }
         }
+        if (rb + 1 == rb1) TILE_STAMP(3);
+        // row sums -> beta_a-weighted total; symmetric pairs: diagonal tile once, strictly-upper tiles twice
+        double acc = sympair ? accd + 2.0 * acc2 : acc2;
+        double tr = sympair ? trd + 2.0 * tr2 : tr2;
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        double v = (t == 0) ? ba * acc : 0.0;
+        if (diag) v = fma(-tr, rowfac, v);                  // trace term (per-lane partial), same warp reduction
+        v = warp_sum(v);
+        if (lane == 0)
+            p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * mm_tile_slots(np) + rb * 8 + warp] = active ? v : 0.0;
     }
-    // row sums -> beta_a-weighted total; symmetric pairs: diagonal tile once, strictly-upper tiles twice
-    double acc = sympair ? accd + 2.0 * acc2 : acc2;
-    double tr = sympair ? trd + 2.0 * tr2 : tr2;
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    double v = (t == 0) ? ba * acc : 0.0;
-    v = warp_sum(v);
-    tr = warp_sum(tr * rowfac);
-    if (lane == 0)
-        p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * mm_tile_slots(np) + rb * 8 + warp] = active ? (v - tr) : 0.0;
+    TILE_STAMP(4);
 }
 
+// rpc = row blocks per CTA (launch_tile chooses it: all of them once the grid still covers the SMs)
 template <int KS, int MINB>
-__global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p) {
+__global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p, int rpc) {
     int a, b;
     pair_decode(blockIdx.y, a, b);
-    if (a != b) mm_tile_body<KS, false, false>(p);
-    else if (p.gp.mode == 0 && p.gp.iK != nullptr) mm_tile_body<KS, true, true>(p);
-    else mm_tile_body<KS, true, false>(p);
+    if (a != b) mm_tile_body<KS, false, false>(p, rpc);
+    else if (p.gp.mode == 0 && p.gp.iK != nullptr) mm_tile_body<KS, true, true>(p, rpc);
+    else mm_tile_body<KS, true, false>(p, rpc);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -644,17 +739,23 @@ __device__ __forceinline__ void mm_finish_device(const MMParams& p, int r) {
     const MMWs& L = p.L;
     const double* wsr = p.ws + (size_t)r * L.per_r;
     const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
-    for (int q = threadIdx.x; q < L.P; q += blockDim.x) {
-        int a, b;
-        pair_decode(q, a, b);
+    // one warp per pair: the lanes fetch the per-row-octet partials in parallel (independent loads, one L2 round
+    // trip) and reduce them in a fixed shuffle tree -- this sits on the serial path of every rollout step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int slots = mm_tile_slots(L.np);
+    for (int q = warp; q < L.P; q += nw) {
         double T = 0.0;
-        const int slots = mm_tile_slots(L.np);
-        for (int k = 0; k < slots; ++k) T += wsr[L.Tpart + (size_t)q * slots + k];
-        const double Ma = p.M[(size_t)r * E + a], Mb = p.M[(size_t)r * E + b];
-        double v = T - Ma * Mb;
-        if (a == b) v += (gp.mode == 0) ? sf2[a] : 1e-6;
-        p.S[((size_t)r * E + a) * E + b] = v;
-        p.S[((size_t)r * E + b) * E + a] = v;
+        for (int k = lane; k < slots; k += 32) T += wsr[L.Tpart + (size_t)q * slots + k];
+        T = warp_sum(T);
+        if (lane == 0) {
+            int a, b;
+            pair_decode(q, a, b);
+            const double Ma = p.M[(size_t)r * E + a], Mb = p.M[(size_t)r * E + b];
+            double v = T - Ma * Mb;
+            if (a == b) v += (gp.mode == 0) ? sf2[a] : 1e-6;
+            p.S[((size_t)r * E + a) * E + b] = v;
+            p.S[((size_t)r * E + b) * E + a] = v;
+        }
     }
 }
 
