@@ -346,7 +346,9 @@ def run_ours(args):
     achieved = flops / (tile_ms * 1e-3) / 1e12
     peak_eff = flops / (dot_flops / dmma_tf + other_flops / dfma_tf)   # time-weighted fp64 peak for this kernel's op mix
     # compulsory bytes per launch: iK once (shared, L2 resident) + per restart zeta, beta, B_q and the per-pair blocks
-    alg_bytes = 8.0 * (E * N * N + R * (N * D + E * N + P * N + P * 552))
+    npad, ks = (N + 63) // 64 * 64, (D + 3) // 4
+    # ... and the row-side operands materialised by setup stage 2 (U' fragments 4*ks doubles + A' per pair and row)
+    alg_bytes = 8.0 * (E * N * N + R * (N * D + E * N + P * N + P * 552 + P * npad * (4 * ks + 1)))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -363,7 +365,7 @@ def run_ours(args):
     roofline = {
         "bound": "tensor", "kernel": "mm_tile_kernel<3,3> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)",
         "achieved": achieved, "peak": peak_eff, "unit": "TFLOP/s", "frac": achieved / peak_eff, "traffic": traffic,
-        "traffic_source": "profiles/r01_mm_tile_ncu_full_final.txt (ncu --set full, same kernel and config)" if traffic else None,
+        "traffic_source": "profiles/r01_s2_mm_tile_ncu_full.txt (ncu --set full, same kernel and config; ncu flushes the caches before the launch, in the pipeline the row operands written by the setup kernel are L2 hits)" if traffic else None,
         "algorithmic_bytes": alg_bytes,
         "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), "
                        "time-weighted for this kernel's op mix; MEASURED_PEAKS.json holds no fp64 figure" % (dfma_tf, dmma_tf),

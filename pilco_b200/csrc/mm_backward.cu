@@ -61,6 +61,10 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     double ua[KS], Apv;
     tile_row_operands<KS>(wsr + L.Qab + (size_t)q * PAIR_BLK, wsr + L.zeta, ldz, row, row < p.gp.n, lane, ua, Apv);
     const double* ikrow = DIAG ? p.gp.iK + ((size_t)a * p.gp.ldk + row) * p.gp.ldk : nullptr;
+    // as in the forward tile kernel: the integer part of A' rides in the exp's rounding constant, the fractional
+    // part (rowfac) scales this row's sums once at the end
+    double am, rowfac;
+    exp_row_split(Apv, am, rowfac);
 
     // accumulators: row sums hL (hK) per lane (quad-reduced at the end) and HV in DMMA C-fragment layout:
     // hv[nt][c] = HV[row g][8 nt + 2t + c], complete sums over the columns (the DMMA reduces over k = column)
@@ -83,13 +87,13 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
         if (active) {
             for (int col = 0; col < cend; col += 8) {
                 const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
-                double e0 = Apv + bq.x, e1 = Apv + bq.y;
+                double e0 = bq.x, e1 = bq.y;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                     const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
                     dmma884(e0, e1, ua[ks], bf);
                 }
-                const double l0 = exp_scaled(e0, tab), l1 = exp_scaled(e1, tab);
+                const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
                 const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                 const double w0 = bb.x * l0, w1 = bb.y * l1;        // W[g][2t], W[g][2t+1]  (C-fragment layout)
                 hl += w0 + w1;
@@ -126,19 +130,19 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     double* out = wsr + bp.B.rowout + ((size_t)q * np + row) * bp.B.ldr;
     hl += __shfl_xor_sync(0xffffffffu, hl, 1);
     hl += __shfl_xor_sync(0xffffffffu, hl, 2);
-    if (t == 0) out[0] = active ? hl : 0.0;
+    if (t == 0) out[0] = active ? hl * rowfac : 0.0;
     if (DIAG) {
         hk += __shfl_xor_sync(0xffffffffu, hk, 1);
         hk += __shfl_xor_sync(0xffffffffu, hk, 2);
-        if (t == 0) out[DP + 1] = active ? hk : 0.0;
+        if (t == 0) out[DP + 1] = active ? hk * rowfac : 0.0;
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int d0 = 8 * nt + 2 * t;
         if (d0 < DP) {
-            out[1 + d0] = active ? hvL[nt][0] : 0.0;
-            out[2 + d0] = active ? hvL[nt][1] : 0.0;
-            if (DIAG) { out[DP + 2 + d0] = active ? hvK[nt][0] : 0.0; out[DP + 3 + d0] = active ? hvK[nt][1] : 0.0; }
+            out[1 + d0] = active ? hvL[nt][0] * rowfac : 0.0;
+            out[2 + d0] = active ? hvL[nt][1] * rowfac : 0.0;
+            if (DIAG) { out[DP + 2 + d0] = active ? hvK[nt][0] * rowfac : 0.0; out[DP + 3 + d0] = active ? hvK[nt][1] * rowfac : 0.0; }
         }
     }
 }

@@ -739,15 +739,19 @@ __device__ __forceinline__ void mm_finish_device(const MMParams& p, int r) {
     const MMWs& L = p.L;
     const double* wsr = p.ws + (size_t)r * L.per_r;
     const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
-    // one warp per pair: the lanes fetch the per-row-octet partials in parallel (independent loads, one L2 round
-    // trip) and reduce them in a fixed shuffle tree -- this sits on the serial path of every rollout step
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // two adjacent lanes per pair: each sums every second per-row-octet partial (independent loads the compiler
+    // pipelines), one shuffle combines them -- this sits on the serial path of every rollout step.  Fixed order:
+    // deterministic.
     const int slots = mm_tile_slots(L.np);
-    for (int q = warp; q < L.P; q += nw) {
+    const int half = threadIdx.x & 1, per_round = blockDim.x >> 1;
+    for (int base = 0; base < L.P; base += per_round) {      // uniform trip count: the shuffle below is warp-wide
+        const int q = base + (threadIdx.x >> 1);
+        const bool valid = q < L.P;
         double T = 0.0;
-        for (int k = lane; k < slots; k += 32) T += wsr[L.Tpart + (size_t)q * slots + k];
-        T = warp_sum(T);
-        if (lane == 0) {
+        if (valid)
+            for (int k = half; k < slots; k += 2) T += wsr[L.Tpart + (size_t)q * slots + k];
+        T += __shfl_xor_sync(0xffffffffu, T, 1);
+        if (valid && half == 0) {
             int a, b;
             pair_decode(q, a, b);
             const double Ma = p.M[(size_t)r * E + a], Mb = p.M[(size_t)r * E + b];
