@@ -207,3 +207,37 @@ def test_oct2py_stand_in_conventions():
     assert len(out) == 4 and isinstance(out[0], float)
     from gpflow import config
     assert config.default_float() is np.float64
+
+
+def test_safe_extension_host_surface():
+    """Host logic of the safe-PILCO drop-ins (no device work): the parameter block handed to the box-risk kernel,
+    the reference's truthiness handling of missing bounds (rewards_safe.py:44-52), reward-term lowering of
+    ObjectiveFunction / SafePILCO (channels, coefficients) and the import paths of the reference package."""
+    from safe_pilco_extension.rewards_safe import RiskOfCollision, SingleConstraint, ObjectiveFunction
+    from safe_pilco_extension.safe_pilco import SafePILCO
+    from pilco.rewards import ExponentialReward, LinearReward, CombinedRewards
+    from pilco.controllers import LinearController
+    from pilco_b200 import _lib
+    inf = float("inf")
+    r = RiskOfCollision(4, [-1.0, -2.0], [1.5, 2.5])
+    assert np.array_equal(r.prm(), [2, 1, 2.0, 0, -1.0, 1.5, 2, -2.0, 2.5])          # dims 0 and 2, scale 2*diag(s)
+    assert np.array_equal(SingleConstraint(3, low=0.2).prm(), [1, 1, 1.0, 3, 0.2, inf])
+    assert np.array_equal(SingleConstraint(1, high=0.7, inside=False).prm(), [1, 0, 1.0, 1, -inf, 0.7])
+    assert np.array_equal(SingleConstraint(1, high=0.7, low=0.0).prm(), [1, 1, 1.0, 1, -inf, 0.7])   # low=0.0 is falsy upstream
+    with pytest.raises(Exception):
+        SingleConstraint(0)
+    obj = ObjectiveFunction(ExponentialReward(4), r, mu=2.0)
+    t = obj.terms(coef=0.5)
+    assert [x["kind"] for x in t] == [_lib.REWARD_EXP, _lib.REWARD_BOX] and [x["coef"] for x in t] == [0.5, -1.0]
+    assert all(x["channel"] == _lib.CHANNEL_ADD for x in t)
+    X = np.random.rand(30, 5); Y = np.random.rand(30, 4)
+    comb = CombinedRewards(4, [LinearReward(4, np.ones(4)), ExponentialReward(4)], coefs=[2.0, 3.0])
+    sp = SafePILCO((X, Y), controller=LinearController(4, 1), reward_add=comb, reward_mult=r, mu=-7.0, horizon=5)
+    terms, mu = sp.reward_spec()
+    assert mu == -7.0 and [x["channel"] for x in terms] == [0, 0, 1] and [x["coef"] for x in terms] == [2.0, 3.0, 1.0]
+    sp.mu.assign(0.75 * sp.mu.numpy())
+    assert sp.reward_spec()[1] == -5.25
+    with pytest.raises(Exception):
+        SafePILCO((X, Y), reward_add=comb)                                      # reward_mult is mandatory (safe_pilco.py:23-24)
+    from pilco.models import PILCO
+    assert PILCO((X, Y)).reward_spec()[1] == 0.0
