@@ -369,6 +369,8 @@ def run_ours(args):
         "algorithmic_bytes": alg_bytes,
         "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), "
                        "time-weighted for this kernel's op mix; MEASURED_PEAKS.json holds no fp64 figure" % (dfma_tf, dmma_tf),
+        "pipe_busy_ncu": "fp64 pipe 26.6 % + DMMA (tensor) pipe 37.9 % of elapsed cycles, top stall math_pipe_throttle "
+                         "(profiles/r01_s2_mm_tile_ncu_full.txt, same kernel/config, R=32)",
         "q_contraction_tflops": dot_flops / (tile_ms * 1e-3) / 1e12,
         "tile_kernel_ms": tile_ms, "setup_kernel_ms": setup_ms,
         "hbm": {"achieved_gbs": alg_bytes / (tile_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
