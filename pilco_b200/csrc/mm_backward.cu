@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     const bool active = row0 < p.gp.n;
     const int ncol8 = (p.gp.n + 7) & ~7;
 
+    TILE_STAMP(0);                                          // (diagnostics build only, see mm_kernels.cuh)
     if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
     __syncthreads();
     auto issue_chunk = [&](int c0, bool with_table) {
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     // part (rowfac) scales this row's sums once at the end
     double am, rowfac;
     exp_row_split(Apv, am, rowfac);
+    TILE_STAMP(1);
 
     // accumulators: row sums hL (hK) per lane (quad-reduced at the end) and HV in DMMA C-fragment layout:
     // hv[nt][c] = HV[row g][8 nt + 2t + c], complete sums over the columns (the DMMA reduces over k = column)
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
         }
         mbar_wait(bar, phase);
         phase ^= 1;
+        if (c0 == 0) TILE_STAMP(2);
         if (active) {
             for (int col = 0; col < cend; col += 8) {
                 const double2 bq = *reinterpret_cast<const double2*>(sBq + col + 2 * t);
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
             }
         }
     }
+    TILE_STAMP(3);
     // outputs per row: [0]=hL, [1..DP]=HVL, [DP+1]=hK, [DP+2..2DP+1]=HVK  (hK/HVK only for DIAG pairs)
     double* out = wsr + bp.B.rowout + ((size_t)q * np + row) * bp.B.ldr;
     hl += __shfl_xor_sync(0xffffffffu, hl, 1);
@@ -145,6 +149,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
             if (DIAG) { out[DP + 2 + d0] = active ? hvK[nt][0] * rowfac : 0.0; out[DP + 3 + d0] = active ? hvK[nt][1] * rowfac : 0.0; }
         }
     }
+    TILE_STAMP(4);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -564,3 +569,10 @@ int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const do
 }
 
 }  // extern "C"
+
+#ifdef PILCO_TILE_TIMING
+// diagnostics build: phase stamps of the LAST backward tile launch (this translation unit's copy of g_tile_timing)
+extern "C" int pilco_debug_btile_timing(long long* host_out, int n) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_tile_timing, sizeof(long long) * (size_t)n);
+}
+#endif
