@@ -17,6 +17,10 @@ torch_port    the same vectorised form in torch fp64 (autograd = gradient oracle
 staged        numpy statement of the *algorithm the CUDA kernels implement* (W-form mean,
               Cholesky-form pair prologue, A+B+u.zeta exponent, staged VJP) so that device
               workspaces can be compared stage by stage.
+safe_port     numpy/torch transcription of the reference's safe_pilco_extension (parity unpinned: the
+              reference has no test or golden vector for it).
+fitc_staged   numpy statement of the FITC training objective with hand-derived adjoints (the algorithm a
+              device SMGPR trainer implements), checked against torch autograd.
 mrun          a small MATLAB-subset interpreter that executes the reference's ``.m`` files
               where they lie under /root/reference (this container only) to pin the
               transcriptions and to generate ``tests/golden/*.npz``.

@@ -195,3 +195,26 @@ def test_safe_extension_ports_agree():
         Wp[idx] += eps; Wm[idx] -= eps
         fd = (float(torch_total(T(Wp))[2].item()) - float(torch_total(T(Wm))[2].item())) / (2 * eps)
         assert abs(fd - float(gW[idx])) < 1e-6 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("N,M,D", [(60, 12, 3), (150, 25, 5)])
+def test_fitc_staged_value_and_gradient(N, M, D):
+    """oracle/fitc_staged.py (numpy statement of the FITC training objective + hand-derived adjoints, the algorithm
+    a device SMGPR trainer implements) against torch autograd on the host training path's loss."""
+    import torch
+    from oracle import fitc_staged
+    from pilco_b200 import gp_training
+    rng = np.random.RandomState(N)
+    X = rng.rand(N, D)
+    y = np.sin(X).dot(rng.rand(D)) + 1e-2 * rng.randn(N)
+    Z = rng.rand(M, D)
+    ell, sf2, sn2 = 0.7 + rng.rand(D), 1.3, 0.05
+    f, g = fitc_staged.fitc_nlml(X, y, Z, ell, sf2, sn2)
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, requires_grad=True)
+    tZ, tl, tf, tn = T(Z), T(ell), T(sf2), T(sn2)
+    loss = gp_training.fitc_loss(torch.tensor(X), torch.tensor(y), tZ, tl, tf, tn)
+    gZ, gl, gf, gn = torch.autograd.grad(loss, [tZ, tl, tf, tn])
+    assert abs(f - float(loss.detach())) < 1e-9 * max(1.0, abs(f))
+    rel = lambda a, b: np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(np.asarray(b))) + 1e-300)
+    assert rel(g["ell"], gl.numpy()) < 1e-8 and rel(g["Z"], gZ.numpy()) < 1e-8
+    assert rel(g["sf2"], gf.numpy()) < 1e-8 and rel(g["sn2"], gn.numpy()) < 1e-8
