@@ -241,3 +241,18 @@ def test_safe_extension_host_surface():
         SafePILCO((X, Y), reward_add=comb)                                      # reward_mult is mandatory (safe_pilco.py:23-24)
     from pilco.models import PILCO
     assert PILCO((X, Y)).reward_spec()[1] == 0.0
+
+
+def test_plain_c_caller_links_and_runs(tmp_path):
+    """The boundary is a C ABI: a C99 translation unit including only include/pilco_b200.h must compile, link against
+    libpilco_b200.so and run its GPU-free calls (tests/host_harness/c_caller.c)."""
+    import subprocess
+    exe = str(tmp_path / "c_caller")
+    libdir = os.path.join(ROOT, "pilco_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "host_harness", "c_caller.c"),
+                           "-L" + libdir, "-l:libpilco_b200.so", "-Wl,-rpath," + libdir])
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
+    out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("abi 2 mm_ws ") and "workspace" in out.stdout
