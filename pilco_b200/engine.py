@@ -457,6 +457,7 @@ class ActionPlan:
 
     def _enqueue(self):
         U = self.U
+        self.info.zero_()                                  # the kernels only OR failure bits into info
         self.m.copy_(self.h_x, non_blocking=True)
         if self.kind == _lib.POLICY_LINEAR:
             check(lib.pilco_linear_action(self.Ds, U, 1, ptr(self.W), 0, ptr(self.b), 0, ptr(self.m), ptr(self.s),
