@@ -188,13 +188,22 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 // table T[j] = 2^(j/EXP_TAB), correctly rounded on the host, uploaded once (exp_table_upload)
 // (one copy per translation unit: the library is built without relocatable device code)
 static __device__ __align__(16) double g_exp_tab[EXP_TAB];
+// One-time per-DEVICE state (table upload, kernel attributes) is keyed on the current device, so a process that
+// drives several GPUs gets it on each of them.
+#define PILCO_MAX_DEVICES 64
+static inline int pilco_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d < PILCO_MAX_DEVICES ? d : PILCO_MAX_DEVICES - 1;
+}
 static int exp_table_upload() {
-    static bool done = false;
-    if (done) return PILCO_OK;
+    static bool done[PILCO_MAX_DEVICES] = {false};
+    const int dev = pilco_current_device();
+    if (done[dev]) return PILCO_OK;
     double h[EXP_TAB];
     for (int j = 0; j < EXP_TAB; ++j) h[j] = (double)exp2l((long double)j / (long double)EXP_TAB);
     if (cudaMemcpyToSymbol(g_exp_tab, h, sizeof(h)) != cudaSuccess) return PILCO_ERR_LAUNCH;
-    done = true;
+    done[dev] = true;
     return PILCO_OK;
 }
 

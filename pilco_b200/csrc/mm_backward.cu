@@ -479,7 +479,8 @@ template <int KS>
 static int launch_btile(const MMBwdParams& bp, cudaStream_t st) {
     const size_t smem = mm_btile_smem_bytes(bp.B.F.np, bp.B.F.ldz);
     { int rc0 = exp_table_upload(); if (rc0) return rc0; }
-    static bool configured = false;
+    static bool configured_dev[PILCO_MAX_DEVICES] = {false};      // function attributes are per device
+    bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {
         const int big = (int)mm_btile_smem_bytes(TILE_CM, 20);
         if (cudaFuncSetAttribute(mm_btile_kernel<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;

@@ -15,9 +15,10 @@ int mm_check_model(const pilco_gp_model* gp) {
 
 template <int KS>
 static int launch_tile(const MMParams& p, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[PILCO_MAX_DEVICES] = {false};      // function attributes are per device
     static int variant = 1;          // 0: 2 CTAs/SM (<=128 regs), 1: 3 CTAs/SM (<=85 regs)
     static int rpc_env = 0;          // 0: automatic
+    bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {
         const char* e = getenv("PILCO_TILE_VARIANT");       // tuning switches
         if (e && e[0] >= '0' && e[0] <= '2') variant = e[0] - '0';
