@@ -128,6 +128,56 @@ def cpu_reference_steps_per_s(wl, reps=2, h_sample=4, threads=None):
     return reps * h_sample / dt, threads, "R=1, %d rollouts of %d steps (of H=%d), factorisations recomputed per step as in the reference" % (reps, h_sample, CFG["H"])
 
 
+_REAL_REF_SCRIPT = r"""
+import json, sys, time
+import numpy as np
+import tensorflow as tf            # noqa: F401  (ImportError -> the caller falls back to the port)
+import gpflow                      # noqa: F401
+from pilco.models import PILCO
+from pilco.controllers import RbfController
+from pilco.rewards import ExponentialReward
+wl = np.load(sys.argv[1]); h, reps = int(sys.argv[2]), int(sys.argv[3])
+Ds, U = wl["Y"].shape[1], wl["X"].shape[1] - wl["Y"].shape[1]
+ctrl = RbfController(Ds, U, int(wl["Xc"].shape[0]), max_action=1.0)
+p = PILCO((wl["X"], wl["Y"]), controller=ctrl, horizon=h, reward=ExponentialReward(Ds, W=wl["W"], t=wl["t"]),
+          m_init=wl["m0"][None], S_init=wl["S0"])
+for i, m in enumerate(p.mgpr.models):
+    m.kernel.lengthscales.assign(wl["ell"][i]); m.kernel.variance.assign(wl["sf2"][i]); m.likelihood.variance.assign(wl["sn2"][i])
+ctrl.set_data((wl["Xc"], wl["Yc"]))
+for i, m in enumerate(ctrl.models):
+    m.kernel.lengthscales.assign(wl["lc"][i])
+p.predict(wl["m0"][None], wl["S0"], h)
+t0 = time.perf_counter()
+for _ in range(reps):
+    p.predict(wl["m0"][None], wl["S0"], h)
+print(json.dumps({"steps_per_s": reps * h / (time.perf_counter() - t0)}))
+"""
+
+
+def real_reference_steps_per_s(wl, reps=2, h_sample=4):
+    """if a reference install ever appears under baseline/_ref (TensorFlow + GPflow + the reference's
+    own ``pilco`` package), time the UNMODIFIED reference through its public API (PILCO.predict, pilco.py:118-136)
+    in a separate interpreter (its package name collides with this repo's alias package).  Returns None when it is
+    not there or does not import -- the normal case: nothing in /opt/wheelhouse provides tensorflow or gpflow."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "pilco")):
+        return None
+    import tempfile
+    try:
+        Xc, Yc, lc = make_policies([0])
+        with tempfile.TemporaryDirectory() as td:
+            np.savez(os.path.join(td, "wl.npz"), Xc=Xc[0], Yc=Yc[0], lc=lc[0], **wl)
+            open(os.path.join(td, "run.py"), "w").write(_REAL_REF_SCRIPT)
+            env = dict(os.environ, PYTHONPATH=ref_dir)
+            out = subprocess.run([sys.executable, os.path.join(td, "run.py"), os.path.join(td, "wl.npz"), str(h_sample), str(reps)],
+                                 capture_output=True, text=True, timeout=900, cwd=td, env=env)
+        if out.returncode != 0:
+            return None
+        return float(json.loads(out.stdout.strip().splitlines()[-1])["steps_per_s"])
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -139,14 +189,19 @@ def run_reference(args):
     t0 = time.perf_counter()
     v, cores, sample = cpu_reference_steps_per_s(wl, reps=max(1, min(args.steps, 3)), h_sample=4)
     dt = time.perf_counter() - t0
+    kind, note = "port", "reference-equivalent CPU restatement (oracle/torch_port.py); TensorFlow/GPflow are not installable offline"
+    real = real_reference_steps_per_s(wl, reps=max(1, min(args.steps, 3)), h_sample=4)
+    if real is not None:
+        v, cores, kind = real, os.cpu_count() or 1, "reference"
+        note = "the unmodified reference from baseline/_ref through PILCO.predict (TensorFlow/GPflow on the host cores)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v * CFG["H"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "metric config N=300 E=10 D=12 H=40 RBF bf=50 (CPU sample: R=1)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference-equivalent CPU restatement (oracle/torch_port.py); TensorFlow/GPflow are not installable offline",
+        "note": note,
     }
     print(json.dumps(line))
 
