@@ -180,10 +180,7 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 // |r| <= ln2/128 so a degree-5 expm1 polynomial is exact to < 1e-16 relative.  10 fp64-pipe
 // instructions + one shared-memory table read; arguments below -700 are clamped (result ~1e-304).
 // ---------------------------------------------------------------------------------------------
-#define EXP_TAB 1024
-#define EXP_SHIFT 10
-#define EXP_SC 1477.3197218702985           // EXP_TAB / ln 2: exponents are carried PRE-SCALED by this factor
-#define EXP_CLAMP (-1032192.0)              // scaled exponent floor (= -698.7 unscaled), hi word 0xC12F8000
+#include "exp_table.cuh"                   // EXP_TAB, EXP_SC, exp_scaled / exp_shifted / exp_row_split
 
 // table T[j] = 2^(j/EXP_TAB), correctly rounded on the host, uploaded once (exp_table_upload)
 // (one copy per translation unit: the library is built without relocatable device code)
@@ -211,61 +208,7 @@ __device__ __forceinline__ void exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = g_exp_tab[j];
 }
 
-// exp(x) for a PRE-SCALED argument xs = x * EXP_SC (the setup kernels fold EXP_SC into A', B, U', so the DMMA
-// delivers xs directly):  xs = 1024 k + j + r',  exp(x) = 2^k T[j] exp(r' ln2/1024),  |r'| <= 1/2.
-// 7 fp64-pipe instructions (3 add, 2 fma, 1 mul, 1 fma) + integer ops + one shared-memory table read.
-__device__ __forceinline__ double exp_scaled(double xs, const double* __restrict__ tab) {
-    // clamp xs >= EXP_CLAMP with ONE integer instruction: for negative doubles a larger magnitude is a larger
-    // high word, positive values (high word < 0x80000000) pass unchanged, NaNs propagate
-    xs = __hiloint2double((int)min((unsigned)__double2hiint(xs), 0xC12F8000u), __double2loint(xs));
-    const double MAGIC = 6755399441055744.0;              // 1.5 * 2^52
-    const double t  = xs + MAGIC;                         // round to integer in the low mantissa bits
-    const int    ki = __double2loint(t);
-    const double kd = t - MAGIC;
-    const double r  = xs - kd;                            // exact, in [-1/2, 1/2]
-    double q = 5.169222938345892e-11;                     // expm1(r s)/r, s = ln2/1024: cubic, x^4 term economised
-    q = fma(q, r, 2.2909785199379098e-07);                // into the x^2 coefficient (max abs error 1.4e-16)
-    q = fma(q, r, 0.0006769015435155716);
-    const double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + ((ki << 3) & ((EXP_TAB - 1) << 3)));
-    const double em1 = q * r;                             // expm1(r ln2/1024), |.| < 3.4e-4
-    const double v = fma(tj, em1, tj);                    // T[j] * exp(.), in [1, 2.01)
-    // scale by 2^k, k = ki >> 10 >= -1008 after the clamp (v normal): one shift + one integer multiply-add
-    int hi;
-    asm("mad.lo.s32 %0, %1, 0x100000, %2;" : "=r"(hi) : "r"(ki >> EXP_SHIFT), "r"(__double2hiint(v)));
-    return __hiloint2double(hi, __double2loint(v));
-}
-
-// exp((c + Ai) / EXP_SC) for a pre-scaled exponent c plus an INTEGER row offset Ai that the caller folds into the
-// rounding constant: am = EXP_MAGIC + Ai (exact for |Ai| < 2^50).  One DADD cheaper than forming c + A first:
-//   t = c + am -> integer field round(c) + Ai;  kd = t - am = round(c);  r = c - kd in [-1/2, 1/2]  (all exact)
-// The caller multiplies the row's accumulated sums by exp((A - Ai)/EXP_SC) once (exp_row_split below).
-// The 2^k exponent is taken with a funnel shift from the 64-bit integer field, so it is right for
-// |c + Ai| < 2^41 (|log-kernel value| < 1.4e9), and clamped below at 2^-1008 (result ~1e-304, i.e. 0).
-#define EXP_MAGIC 6755399441055744.0                      // 1.5 * 2^52
-__device__ __forceinline__ double exp_shifted(double c, double am, const double* __restrict__ tab) {
-    const double t  = c + am;
-    const int    lo = __double2loint(t), hi = __double2hiint(t);
-    const double kd = t - am;
-    const double r  = c - kd;
-    double q = 5.169222938345892e-11;                     // expm1(r s)/r, s = ln2/1024: cubic, x^4 term economised
-    q = fma(q, r, 2.2909785199379098e-07);                // into the x^2 coefficient (max abs error 1.4e-16)
-    q = fma(q, r, 0.0006769015435155716);
-    const double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + ((lo << 3) & ((EXP_TAB - 1) << 3)));
-    const double em1 = q * r;
-    const double v = fma(tj, em1, tj);
-    int k = (int)__funnelshift_r((unsigned)lo, (unsigned)hi, EXP_SHIFT);   // bits 10..41 of the integer field
-    k = max(k, -1008);
-    int vh;
-    asm("mad.lo.s32 %0, %1, 0x100000, %2;" : "=r"(vh) : "r"(k), "r"(__double2hiint(v)));
-    return __hiloint2double(vh, __double2loint(v));
-}
-// split a pre-scaled row exponent A into am = EXP_MAGIC + rint(A) and the row factor exp((A - rint(A))/EXP_SC)
-__device__ __forceinline__ void exp_row_split(double A, double& am, double& rowfac) {
-    const double Ai = rint(A);
-    am = EXP_MAGIC + Ai;
-    const double y = (A - Ai) * (1.0 / EXP_SC);           // |y| <= 0.5/EXP_SC = 3.4e-4: degree-4 Taylor, error < 4e-20
-    rowfac = fma(y, fma(y, fma(y, fma(y, 1.0 / 24.0, 1.0 / 6.0), 0.5), 1.0), 1.0);
-}
+// (exp_scaled, exp_shifted, exp_row_split: exp_table.cuh -- shared with the host test build)
 
 // ---------------------------------------------------------------------------------------------
 // DMMA: D(8x8) = A(8x4) * B(4x8) + C, fp64 (legacy mma.sync path -- tcgen05 has no f64 kind).

@@ -256,3 +256,52 @@ def test_plain_c_caller_links_and_runs(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.startswith("abi 2 mm_ws ") and "workspace" in out.stdout
+
+
+def test_table_exp_on_host(tmp_path):
+    """pilco_b200/csrc/exp_table.cuh (the 7-instruction table exp of the tile kernels, shared source) compiled for
+    the host: accuracy against libm over the range a log-kernel value can take, the row-offset form used by the
+    tile rows, and the clamp that turns padding (NEG_PAD) and far-apart centres into ~1e-304 instead of garbage."""
+    import subprocess
+    so = str(tmp_path / "exp_harness.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-o", so,
+                           os.path.join(ROOT, "tests", "host_harness", "exp_harness.cpp")])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    c = lambda a: a.ctypes.data_as(dp)
+    lib.exp_harness_scale.restype = ctypes.c_double
+    SC = lib.exp_harness_scale()
+    assert abs(SC - 1024.0 / np.log(2.0)) < 1e-9
+    tab = np.zeros(1024)
+    lib.exp_harness_table(c(tab))
+    assert tab[0] == 1.0 and abs(tab[512] - np.sqrt(2.0)) < 3e-16
+    rng = np.random.RandomState(0)
+    LD = np.longdouble                                          # x87 extended precision: reference for 2^(xs/1024)
+    ref_of = lambda xs: np.exp2(LD(xs) / LD(1024.0))
+    xs = np.concatenate([rng.uniform(-690.0, 1.0, 200000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -1.0, 1.0]]) * SC
+    out = np.zeros_like(xs)
+    lib.exp_harness_scaled(len(xs), c(xs), c(tab), c(out))
+    rel = np.abs((LD(out) - ref_of(xs)) / ref_of(xs)).astype(np.float64)
+    assert rel.max() < 4e-16, rel.max()                       # observed 3.5e-16 (1.6 ulp): table rounding + polynomial + final rounding
+    # row-offset form: c = pre-scaled column part, A = pre-scaled row part (integer part folded into the magic constant)
+    for A in (-123456.789, 0.25, 3210.5, -0.49999):
+        cc = rng.uniform(-400.0, 10.0, 50000) * SC
+        o2 = np.zeros_like(cc)
+        rf = ctypes.c_double()
+        lib.exp_harness_shifted(len(cc), c(cc), ctypes.c_double(A), c(tab), c(o2), ctypes.byref(rf))
+        tot = LD(cc) + LD(A)                                    # exact pre-scaled exponent of the element
+        keep = np.asarray(tot / LD(SC) > -690.0)
+        ref2 = np.exp2(tot[keep] / LD(1024.0))
+        assert np.abs((LD(o2[keep]) - ref2) / ref2).astype(np.float64).max() < 7e-16      # + the row-factor product and its own rounding
+        assert abs(rf.value - np.exp((A - np.rint(A)) / SC)) < 2.3e-16
+    # clamp: padding (NEG_PAD = -1e9 pre-scaled) and extreme negatives give a tiny positive number, never NaN/inf/negative
+    bad = np.array([-1.0e9, -5.0e6, -1.1e6, -1.0e12])
+    o3 = np.zeros_like(bad)
+    rf = ctypes.c_double()
+    lib.exp_harness_shifted(len(bad), c(bad), ctypes.c_double(0.0), c(tab), c(o3), ctypes.byref(rf))
+    assert np.all(np.isfinite(o3)) and np.all(o3 >= 0.0) and np.all(o3 < 1e-300)
+    lib.exp_harness_shifted(len(bad), c(np.zeros(4)), ctypes.c_double(-1.0e9), c(tab), c(o3), ctypes.byref(rf))   # padded ROW
+    assert np.all(np.isfinite(o3)) and np.all(o3 >= 0.0) and np.all(o3 < 1e-300)
+    xneg = np.array([-2000.0, -1e5]) * SC; o4 = np.zeros(2)
+    lib.exp_harness_scaled(2, c(xneg), c(tab), c(o4))
+    assert np.all(np.isfinite(o4)) and np.all(o4 >= 0.0) and np.all(o4 < 1e-300)
