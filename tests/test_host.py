@@ -305,3 +305,46 @@ def test_table_exp_on_host(tmp_path):
     xneg = np.array([-2000.0, -1e5]) * SC; o4 = np.zeros(2)
     lib.exp_harness_scaled(2, c(xneg), c(tab), c(o4))
     assert np.all(np.isfinite(o4)) and np.all(o4 >= 0.0) and np.all(o4 < 1e-300)
+
+
+def test_workspace_layouts_on_host(tmp_path):
+    """Workspace layouts (csrc/mm_kernels.cuh, mm_backward.cuh) compiled for the host: arrays are laid out in
+    ascending, non-overlapping, 16-byte aligned order with the documented sizes, the per-restart stride matches what
+    the shared library reports through pilco_mm_workspace_bytes / pilco_mm_bwd_workspace_bytes, and the pair
+    indexing helpers invert each other."""
+    import subprocess
+    from pilco_b200 import _lib
+    so = str(tmp_path / "layout_harness.so")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-x", "c++", "-I/usr/local/cuda/include", "-o", so,
+                           os.path.join(ROOT, "tests", "host_harness", "layout_harness.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.layout_bwd_per_r.restype = ctypes.c_ulonglong
+    buf = (ctypes.c_ulonglong * 10)()
+    for n, D, E in [(300, 12, 10), (37, 1, 1), (64, 4, 3), (600, 3, 2), (500, 10, 8), (200, 12, 10), (50, 10, 2), (65, 13, 2)]:
+        for ordered in (0, 1):
+            np_ = lib.layout_mm(n, D, E, ordered, buf)
+            zeta, betap, Bq, Tpart, Wm, Wc, Qab, Ufrag, Arow, per_r = [int(v) for v in buf]
+            assert np_ == (n + 63) // 64 * 64 == _lib.lib.pilco_pad_n(n)
+            P = E * E if ordered else E * (E + 1) // 2
+            ldz, ks = ctypes.c_int(), ctypes.c_int()
+            lib.layout_misc(D, ctypes.byref(ldz), ctypes.byref(ks))
+            assert ldz.value >= D and ldz.value % 4 == 0 and ks.value == (D + 3) // 4
+            order = [zeta, betap, Bq, Tpart, Wm, Wc, Qab, Ufrag, Arow, per_r]
+            assert order == sorted(order) and zeta == 0
+            assert betap - zeta == np_ * ldz.value and Bq - betap == E * np_ and Tpart - Bq == P * np_
+            assert Wm - Tpart >= P * (np_ // 8) and Wm % 2 == 0 and Ufrag % 2 == 0 and per_r % 2 == 0
+            assert Qab - Wc >= E and Ufrag - Qab >= P * (2 * 16 * 16 + 2 * 16 + 8)
+            if ordered:
+                assert Ufrag == Arow == per_r or per_r - Arow <= 1                     # backward derives row operands in-kernel
+            else:
+                assert Arow - Ufrag == P * (np_ // 8) * ks.value * 32 and per_r - Arow >= P * np_
+                for R in (1, 7):
+                    assert _lib.lib.pilco_mm_workspace_bytes(n, D, E, R) == per_r * R * 8
+        for need in (0, 1):
+            assert _lib.lib.pilco_mm_bwd_workspace_bytes(n, D, E, 3, need) == lib.layout_bwd_per_r(n, D, E, need) * 3 * 8
+    a, b = ctypes.c_int(), ctypes.c_int()
+    seen = set()
+    for q in range(136):                                                            # E = 16: 136 unordered pairs
+        assert lib.layout_pair(q, ctypes.byref(a), ctypes.byref(b)) == q and 0 <= a.value <= b.value < 16
+        seen.add((a.value, b.value))
+    assert len(seen) == 136
