@@ -57,7 +57,7 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, build_dir=None):
         if verbose and out:
             sys.stderr.write(out)
     out_lib = lib or LIB
-    cmd = [nvcc, "-shared", "-o", out_lib] + objs + ["-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_lib] + objs + ["-lcudart"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout)
