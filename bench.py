@@ -270,11 +270,11 @@ def run_ours(args):
     nsplit = max(1, min(args.nsplit, R))
     pgps = {}
 
-    def make_plan(lo, hi):
+    def make_plan(lo, hi, grad=False):
         pg = engine.gp_factorize(Xc[lo:hi], Yc[lo:hi], lc[lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
         pgps[(lo, hi)] = pg
         sp = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
-        return engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo)
+        return engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo, grad=grad)
 
     split = engine.SplitRollout(make_plan, R, nsplit=nsplit)
     plan = split.plans[0]
@@ -340,7 +340,7 @@ def run_ours(args):
         return float(t.item()) / K                             # ms per step
 
     # ---- forward + reverse sweep (policy gradient), device resident: extra line, not the headline -----------
-    split3 = engine.SplitRollout(make_plan, R, nsplit=nsplit, backward=True) if args.with_backward else None
+    split3 = engine.SplitRollout(lambda lo, hi: make_plan(lo, hi, grad=True), R, nsplit=nsplit, backward=True) if args.with_backward else None
 
     def step_fwd_bwd():
         split3.replay()

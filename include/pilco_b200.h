@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PILCO_ABI_VERSION 2
+#define PILCO_ABI_VERSION 3
 #define PILCO_MAX_D 16          /* max GP input dimension (state+control) */
 #define PILCO_MAX_E 16          /* max number of GP outputs */
 
@@ -76,6 +76,21 @@ int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const do
                       const double* gM, const double* gS, const double* gV,
                       double* gm, double* gs, double* gX, double* gbeta, double* gell,
                       void* ws, size_t ws_bytes, pilco_stream_t stream);
+
+/* Taped moment match: pilco_mm_forward that also leaves, per unordered output pair (a,b), the row sums, column sums
+ * and the product (G_ab o L'_ab) Z of the N x N matrix it has in registers anyway (Z = centred inputs) on a tape;
+ * pilco_mm_backward_taped turns the tape and the cotangents into gm, gs WITHOUT recomputing an exponential.
+ * Only the cotangents of the input moments are produced (the dynamics GP of the policy objective, whose inputs
+ * and hyper-parameters are constants, pilco/models/pilco.py:80-82); trainable centres need pilco_mm_backward. */
+size_t pilco_mm_tape_bytes(int n, int D, int E, int R);          /* 0 if n > 2048 */
+size_t pilco_mm_tape_bwd_workspace_bytes(int D, int E, int R);
+int pilco_mm_forward_taped(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                           double* M, double* S, double* V, int* info,
+                           void* ws, size_t ws_bytes, void* tape, size_t tape_bytes, pilco_stream_t stream);
+int pilco_mm_backward_taped(const pilco_gp_model* gp, int R, const double* m, const double* s, const double* M,
+                            const double* gM, const double* gS, const double* gV,
+                            const void* tape, size_t tape_bytes, double* gm, double* gs,
+                            void* ws, size_t ws_bytes, pilco_stream_t stream);
 
 /* ---- GP factorisation -----------------------------------------------------------------------
  * Replaces MGPR.calculate_factorizations (pilco/models/mgpr.py:81-89; gp0.m:46-61):
@@ -207,9 +222,15 @@ typedef struct pilco_rollout {
     void* ws; size_t ws_bytes;
     double mult_mu;             /* SafePILCO.mu (safe_pilco.py:26,49); ignored without MULT terms */
     double* step_risk;          /* [R,H] per-step risk of the MULT channel, or NULL */
+    /* Tape of the dynamics moment match (pilco_rollout_tape_bytes, 16-byte aligned) or NULL.  With a tape the forward
+     * cascade runs the TAPED tile pass (pilco_mm_forward_taped) at every step and pilco_rollout_backward consumes
+     * the tape instead of recomputing any N x N exponential: forward+backward cost ~1.9 forward tile passes instead
+     * of ~5.  Without it pilco_rollout_backward recomputes (memory-lean path, same results). */
+    void* tape; size_t tape_bytes;
 } pilco_rollout;
 
 size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro);
+size_t pilco_rollout_tape_bytes(const pilco_rollout* ro);   /* 0: shape not supported by the taped pass (n > 2048) */
 int    pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream);
 
 /* Reverse sweep: gradient of ro->reward[r] (= sum_t E[r(x_t)], the negative of PILCO.training_loss,

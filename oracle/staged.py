@@ -151,6 +151,83 @@ def mm_backward_staged(C, ell, sf2, beta, iK, m, s, gM, gS, gV, mode=0):
     return gm, _sym(gs), gzeta, gbeta, gell
 
 
+def mm_tape_forward(C, ell, sf2, beta, iK, m, s, mode=0):
+    """What the TAPED forward tile pass leaves per unordered pair (a <= b) (device: mm_tape.cuh):
+    Q, Cm, logdetR and, of H = G o L' (unweighted by any cotangent), the row sums hr, the column sums hc and the
+    product H Z.  Returns a dict keyed by (a, b)."""
+    E, D = ell.shape
+    s = _sym(s)
+    zeta = C - m
+    p = 1.0 / ell ** 2
+    lsf2 = np.log(sf2)
+    k = lsf2[:, None] - 0.5 * (p[:, None, :] * zeta[None] ** 2).sum(-1)
+    tape = {}
+    for b in range(E):
+        for a in range(b + 1):
+            Q, Cm, logdetR = pair_setup(s, p[a], p[b])
+            za, zb = zeta * p[a], zeta * p[b]
+            Ua = 2.0 * (za @ Q) * p[b]
+            Ap = k[a] + ((za @ Q) * za).sum(1) - 0.5 * logdetR
+            Bq = k[b] + ((zb @ Q) * zb).sum(1)
+            Lp = np.exp(Ap[:, None] + Bq[None, :] + Ua @ zeta.T)
+            G = np.outer(beta[a], beta[b])
+            if a == b and mode == 0:
+                G = G - iK[a]
+            H = G * Lp
+            tape[(a, b)] = dict(Q=Q, Cm=Cm, logdetR=logdetR, hr=H.sum(1), hc=H.sum(0), HZ=H @ zeta)
+    return tape
+
+
+def mm_backward_tape(C, ell, sf2, beta, m, s, gM, gS, gV, tape):
+    """VJP of the moment match w.r.t. the input moments only, from the tape (device: mm_tape_bfinish_kernel).
+    Unordered pairs, both sides at once; no exponential of the N x N part is recomputed.
+    Returns gm [D], gs [D,D] (symmetric part) -- equal to the first two results of mm_backward_staged."""
+    E, D = ell.shape
+    s = _sym(s)
+    zeta = C - m
+    p = 1.0 / ell ** 2
+    lsf2 = np.log(sf2)
+    gm = np.zeros(D)
+    gs = np.zeros((D, D))
+    # mean / V block: weighted moment sums with u_n = gw_n w_n, v_n = w_n
+    Wm, M = [], np.zeros(E)
+    for a in range(E):
+        A = s + np.diag(ell[a] ** 2)
+        W = np.linalg.inv(A)
+        q = np.exp(-0.5 * ((zeta @ W) * zeta).sum(1))
+        c = np.exp(lsf2[a] + 0.5 * np.log(ell[a] ** 2).sum() - 0.5 * np.linalg.slogdet(A)[1])
+        Wm.append((W, beta[a] * q * c))
+        M[a] = Wm[a][1].sum()
+    gMtot = gM - (gS + gS.T) @ M
+    for a in range(E):
+        W, w = Wm[a]
+        wgv = W @ gV[:, a]
+        u = (gMtot[a] + zeta @ wgv) * w
+        A1 = (zeta * u[:, None]).T @ zeta
+        y1, y2 = zeta.T @ u, zeta.T @ w
+        gW = -0.5 * A1 + _sym(np.outer(gV[:, a], y2))
+        gs += -W @ gW @ W - 0.5 * u.sum() * W
+        gm += W @ y1 - w.sum() * wgv
+    # covariance block
+    for b in range(E):
+        for a in range(b + 1):
+            t = tape[(a, b)]
+            g = gS[a, a] if a == b else gS[a, b] + gS[b, a]
+            Q, Cm, hr, hc, HZ = t["Q"], t["Cm"], t["hr"], t["hc"], t["HZ"]
+            delta = p[a] + p[b]
+            A1 = (zeta * hr[:, None]).T @ zeta
+            A2 = (zeta * hc[:, None]).T @ zeta
+            A3 = zeta.T @ HZ
+            Pa, Pb = np.diag(p[a]), np.diag(p[b])
+            X3 = Pa @ A3 @ Pb
+            gQ = g * (Pa @ A1 @ Pa + Pb @ A2 @ Pb + X3 + X3.T)
+            glogR = -0.5 * g * hr.sum()
+            gs += 0.5 * Cm @ (gQ / delta[:, None] / delta[None, :]) @ Cm + glogR * Cm
+            u = p[a] * (zeta.T @ hr) + p[b] * (zeta.T @ hc)
+            gm += g * (u - 2.0 * delta * (Q @ u))
+    return gm, _sym(gs)
+
+
 # ---- closed forms -----------------------------------------------------------------------------------
 def squash_forward(m, s, e):
     d = np.diag(s)

@@ -44,7 +44,8 @@ class Rollout(C.Structure):
                 ("m0", c_dp), ("m0_bs", c_ll), ("S0", c_dp), ("S0_bs", c_ll),
                 ("traj_m", c_dp), ("traj_S", c_dp), ("reward", c_dp), ("step_reward", c_dp),
                 ("info", c_dp), ("ws", c_dp), ("ws_bytes", C.c_size_t),
-                ("mult_mu", C.c_double), ("step_risk", c_dp)]
+                ("mult_mu", C.c_double), ("step_risk", c_dp),
+                ("tape", c_dp), ("tape_bytes", C.c_size_t)]
 
 
 class RolloutGrad(C.Structure):
@@ -56,7 +57,7 @@ class RolloutGrad(C.Structure):
 POLICY_LINEAR, POLICY_RBF = 0, 1
 REWARD_EXP, REWARD_LINEAR, REWARD_BOX = 0, 1, 2
 CHANNEL_ADD, CHANNEL_MULT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); every symbol declared in include/pilco_b200.h
 SIGNATURES = {
@@ -79,6 +80,13 @@ SIGNATURES = {
     "pilco_exp_reward": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 8),
     "pilco_box_risk": (C.c_int, [C.c_int, C.c_int] + [c_dp] * 7),
     "pilco_rollout_workspace_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
+    "pilco_rollout_tape_bytes": (C.c_size_t, [C.POINTER(Rollout)]),
+    "pilco_mm_tape_bytes": (C.c_size_t, [C.c_int] * 4),
+    "pilco_mm_tape_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "pilco_mm_forward_taped": (C.c_int, [C.POINTER(GpModel), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                         c_dp, C.c_size_t, c_dp, C.c_size_t, c_dp]),
+    "pilco_mm_backward_taped": (C.c_int, [C.POINTER(GpModel), C.c_int] + [c_dp] * 6 + [c_dp, C.c_size_t, c_dp, c_dp,
+                                                                                  c_dp, C.c_size_t, c_dp]),
     "pilco_rollout_forward": (C.c_int, [C.POINTER(Rollout), c_dp]),
     "pilco_mm_bwd_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "pilco_mm_backward": (C.c_int, [C.POINTER(GpModel), C.c_int] + [c_dp] * 11 + [c_dp, C.c_size_t, c_dp]),

@@ -182,27 +182,19 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 // ---------------------------------------------------------------------------------------------
 #include "exp_table.cuh"                   // EXP_TAB, EXP_SC, exp_scaled / exp_shifted / exp_row_split
 
-// table T[j] = 2^(j/EXP_TAB), correctly rounded on the host, uploaded once (exp_table_upload)
+// table T[j] = 2^(j/EXP_TAB), correctly rounded (scripts/gen_exp_table.py), compiled into the library: no run-time
+// upload, no per-device state, so every entry point is CUDA-graph capturable from its first call
 // (one copy per translation unit: the library is built without relocatable device code)
-static __device__ __align__(16) double g_exp_tab[EXP_TAB];
-// One-time per-DEVICE state (table upload, kernel attributes) is keyed on the current device, so a process that
-// drives several GPUs gets it on each of them.
+static __device__ __align__(16) const double g_exp_tab[EXP_TAB] = {
+#include "exp_table_data.inc"
+};
 #define PILCO_MAX_DEVICES 64
 static inline int pilco_current_device() {
     int d = 0;
     if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
     return d < PILCO_MAX_DEVICES ? d : PILCO_MAX_DEVICES - 1;
 }
-static int exp_table_upload() {
-    static bool done[PILCO_MAX_DEVICES] = {false};
-    const int dev = pilco_current_device();
-    if (done[dev]) return PILCO_OK;
-    double h[EXP_TAB];
-    for (int j = 0; j < EXP_TAB; ++j) h[j] = (double)exp2l((long double)j / (long double)EXP_TAB);
-    if (cudaMemcpyToSymbol(g_exp_tab, h, sizeof(h)) != cudaSuccess) return PILCO_ERR_LAUNCH;
-    done[dev] = true;
-    return PILCO_OK;
-}
+static inline int exp_table_upload() { return PILCO_OK; }       // (kept for the launchers: nothing to upload)
 
 __device__ __forceinline__ void exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = g_exp_tab[j];

@@ -1,6 +1,6 @@
 // mm_forward.cu -- host side of pilco_mm_forward (C ABI) + shared launcher.
 #include <stdlib.h>
-#include "mm_kernels.cuh"
+#include "mm_tape.cuh"
 
 int mm_check_model(const pilco_gp_model* gp) {
     if (!gp || !gp->X || !gp->ell || !gp->sf2 || !gp->beta) return PILCO_ERR_NULL;
@@ -60,7 +60,8 @@ int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
     }
     CUDA_LAUNCH_CHECK();
     int rc;
-    switch (ks) {
+    if (p.tape != nullptr) rc = mm_tape_tile_launch(p, st);      // taped forward: same sums + what the reverse sweep needs
+    else switch (ks) {
         case 1: rc = launch_tile<1>(p, st); break;
         case 2: rc = launch_tile<2>(p, st); break;
         case 3: rc = launch_tile<3>(p, st); break;

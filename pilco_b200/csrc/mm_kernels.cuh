@@ -49,6 +49,9 @@ static inline __host__ __device__ MMWs mm_ws_layout(int n, int D, int E, bool or
     return L;
 }
 
+// layout of the tape of one taped moment-match call (mm_tape.cuh), offsets in doubles per restart
+struct MMTapeL { size_t Q, C, Ld, hr, hc, HZ, per_r; int cs, ldh, np, P; };
+
 struct MMParams {
     pilco_gp_model gp;
     int R;
@@ -62,6 +65,10 @@ struct MMParams {
     // logdet R_ab per pair; offsets (doubles, per restart) of those arrays inside ws.  bwd==0: unused.
     int bwd;
     size_t oQ, oC, oLd;
+    // taped forward (mm_tape.cuh): tape != nullptr -> setup stage 1 also stores Q, C, logdet R per unordered pair and
+    // the taped tile kernel runs in place of mm_tile_kernel
+    double* tape = nullptr;
+    MMTapeL TL;
 };
 
 
@@ -238,9 +245,10 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p)
         Qo2[PAIR_SC + 2] = log(sf2[b]);
         if (!ok && p.info) atomicOr(&p.info[r], 1);
     }
-    if (BWD) {
-        double* Qo = wsr + p.oQ + (size_t)q * D * D;
-        double* Co = wsr + p.oC + (size_t)q * D * D;
+    if (BWD || p.tape != nullptr) {
+        double* tpr = BWD ? nullptr : p.tape + (size_t)r * p.TL.per_r;
+        double* Qo = BWD ? wsr + p.oQ + (size_t)q * D * D : tpr + p.TL.Q + (size_t)q * D * D;
+        double* Co = BWD ? wsr + p.oC + (size_t)q * D * D : tpr + p.TL.C + (size_t)q * D * D;
         double c[DP];
 #pragma unroll
         for (int i = 0; i < DP; ++i) c[i] = (i == li) ? 1.0 : 0.0;
@@ -250,7 +258,7 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p)
             for (int i = 0; i < DP; ++i)
                 if (i < D) { Qo[i * D + lane] = qsym[i]; Co[i * D + lane] = c[i]; }
         }
-        if (lane == 0) wsr[p.oLd + q] = ldet;
+        if (lane == 0) { if (BWD) wsr[p.oLd + q] = ldet; else tpr[p.TL.Ld + q] = ldet; }
     }
 }
 
@@ -348,9 +356,9 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
     }
 
     // ---------------- pair task: column-side exponent piece B_ab[m] = k_b[m] + z_b' Q z_b (pre-scaled) --------
-    // (Q diag p_b) zeta_m for 8 centres at a time as a small fp64-DMMA GEMM Z[8 x DP] . Qb^T; the row-side
-    // pieces A'_ab[n], U'_ab[n] are NOT materialised: every tile CTA derives them for its own 64 rows
-    // (tile_row_operands below).
+    // (Q diag p_b) zeta_m for 8 centres at a time as a small fp64-DMMA GEMM Z[8 x DP] . Qb^T.  Forward mode also
+    // materialises the row-side pieces A'_ab[n], U'_ab[n] of the same 8 centres (Ufrag / Arow, read once by the
+    // tile kernel); the ordered-pair backward mode leaves them to the backward tile kernel's prologue.
     const int q = task - E;
     int a, b;
     if (BWD) { a = q / E; b = q % E; } else pair_decode(q, a, b);

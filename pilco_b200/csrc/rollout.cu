@@ -8,6 +8,7 @@
 //   mm_setup / mm_tile on the dynamics GP with the joint Gaussian of step t
 // and a final ro_state<H> that closes the last step.
 #include "rollout.cuh"
+#include "mm_tape.cuh"
 #include "small_kernels.cuh"
 
 struct RoDev {
@@ -146,12 +147,24 @@ size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro) {
     return ro_ws_layout(ro).total * sizeof(double);
 }
 
+size_t pilco_rollout_tape_bytes(const pilco_rollout* ro) {
+    if (!ro || ro->R < 1 || ro->H < 0) return 0;
+    if (pad64(ro->dyn.n) > TAPE_MAX_NP || ro->dyn.D < 1 || ro->dyn.D > MAXD || ro->dyn.E < 1 || ro->dyn.E > MAXE) return 0;
+    return mm_tape_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R).per_r * (size_t)ro->R * (size_t)ro->H * sizeof(double);
+}
+
 int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
     int rc = ro_check(ro);
     if (rc) return rc;
     const RoWs L = ro_ws_layout(ro);
     if (ro->ws_bytes < L.total * sizeof(double)) return PILCO_ERR_WORKSPACE;
     if (((uintptr_t)ro->ws) & 15) return PILCO_ERR_ALIGN;
+    if (ro->tape) {
+        const size_t need = pilco_rollout_tape_bytes(ro);
+        if (need == 0 && ro->H > 0) return PILCO_ERR_UNSUPPORTED;
+        if (ro->tape_bytes < need) return PILCO_ERR_WORKSPACE;
+        if (((uintptr_t)ro->tape) & 15) return PILCO_ERR_ALIGN;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     double* ws = (double*)ro->ws;
     const int R = ro->R, H = ro->H, Ds = ro->pol.Ds, U = ro->pol.U, D = Ds + U;
@@ -174,6 +187,10 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
         p.m = slot(L.mj, D, t); p.s = slot(L.sj, (size_t)D * D, t); p.m_rs = D; p.s_rs = (long long)D * D;
         p.M = slot(L.Md, Ds, t); p.S = slot(L.Sd, (size_t)Ds * Ds, t); p.V = slot(L.Vd, (size_t)D * Ds, t);
         p.info = ro->info; p.ws = ws + L.dynws; p.L = mm_ws_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
+        if (ro->tape) {                                  // taped tile pass: slot (t, :) of the rollout's tape
+            p.TL = mm_tape_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E, R);
+            p.tape = (double*)ro->tape + (size_t)t * RR * p.TL.per_r;
+        }
         return p;
     };
     auto pol_params = [&](int t) {

@@ -12,6 +12,7 @@
 //   mm_backward (RBF policy GP, accumulating) -> adds to (gm_t, gS_t) and to g(centres), g(beta), g(lengthscales)
 // then, for the RBF policy, the VJP through beta = (K + sn2 I)^-1 Y.
 #include "mm_backward.cuh"
+#include "mm_tape.cuh"
 #include "rollout.cuh"
 #include "small_kernels.cuh"
 
@@ -33,7 +34,10 @@ static RbWs rb_ws_layout(const pilco_rollout* ro) {
     L.gMp = take(U); L.gSp = take(U * U); L.gVp = take(Ds * U);
     const size_t bf = ro->pol.kind == PILCO_POLICY_RBF ? ro->pol.rbf.n : 0;
     L.gbeta = take(U * bf); L.gy = take(U * bf);
-    L.dynb = o; o += pilco_mm_bwd_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R, 0) / 8;
+    // dynamics GP: task partials of the tape-driven reverse sweep, or the workspace of the recomputing one
+    L.dynb = o;
+    if (ro->tape) o += ((size_t)ro->R * mm_tape_bwd_part_doubles(ro->dyn.D, ro->dyn.E) + 1) & ~(size_t)1;
+    else o += pilco_mm_bwd_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R, 0) / 8;
     L.polb = o;
     if (ro->pol.kind == PILCO_POLICY_RBF)
         o += pilco_mm_bwd_workspace_bytes(ro->pol.rbf.n, ro->pol.rbf.D, ro->pol.rbf.E, ro->R, 1) / 8;
@@ -264,10 +268,22 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
         d.Vu = slot(FL.Vu, (size_t)Ds * U, t);
         rb_pre_kernel<<<R, 128, 0, st>>>(d);
         CUDA_LAUNCH_CHECK();
-        MMBwdParams bp = mm_bwd_params(&ro->dyn, R, slot(FL.mj, D, t), D, slot(FL.sj, (size_t)D * D, t), (long long)D * D,
-                                       slot(FL.Md, Ds, t), d.gMd, d.gSd, d.gVd,
-                                       d.gmj, D, d.gsj, (long long)D * D, nullptr, nullptr, nullptr, 0, bws + BL.dynb);
-        rc = mm_backward_launch(bp, st);
+        if (ro->tape) {                              // consume the tape of step t: no exponential is recomputed
+            MMTapeBwd tb;
+            tb.gp = ro->dyn; tb.R = R;
+            tb.m = slot(FL.mj, D, t); tb.m_rs = D; tb.s = slot(FL.sj, (size_t)D * D, t); tb.s_rs = (long long)D * D;
+            tb.Mfwd = slot(FL.Md, Ds, t); tb.gM = d.gMd; tb.gS = d.gSd; tb.gV = d.gVd;
+            tb.TL = mm_tape_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E, R);
+            tb.tape = (const double*)ro->tape + (size_t)t * RR * tb.TL.per_r;
+            tb.part = bws + BL.dynb;
+            tb.gm = d.gmj; tb.gm_rs = D; tb.gs = d.gsj; tb.gs_rs = (long long)D * D; tb.accumulate = 0;
+            rc = mm_tape_backward_launch(tb, st);
+        } else {
+            MMBwdParams bp = mm_bwd_params(&ro->dyn, R, slot(FL.mj, D, t), D, slot(FL.sj, (size_t)D * D, t), (long long)D * D,
+                                           slot(FL.Md, Ds, t), d.gMd, d.gSd, d.gVd,
+                                           d.gmj, D, d.gsj, (long long)D * D, nullptr, nullptr, nullptr, 0, bws + BL.dynb);
+            rc = mm_backward_launch(bp, st);
+        }
         if (rc) return rc;
         rb_post_kernel<<<R, 128, 0, st>>>(d);
         CUDA_LAUNCH_CHECK();

@@ -195,6 +195,43 @@ def mm_backward(gp, m, s, M, gM, gS, gV, need_param=False):
     return gm, gs, gX, gb, gl
 
 
+def mm_forward_taped(gp, m, s):
+    """pilco_mm_forward_taped: as mm_forward, plus the tape (opaque device buffer) for mm_backward_taped."""
+    m, s = dev(m), dev(s)
+    R = m.shape[0]
+    d = device()
+    M = torch.empty((R, gp.E), dtype=F64, device=d)
+    S = torch.empty((R, gp.E, gp.E), dtype=F64, device=d)
+    V = torch.empty((R, gp.D, gp.E), dtype=F64, device=d)
+    info = torch.zeros(R, dtype=torch.int32, device=d)
+    wsb = lib.pilco_mm_workspace_bytes(gp.n, gp.D, gp.E, R)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    tb = lib.pilco_mm_tape_bytes(gp.n, gp.D, gp.E, R)
+    if tb == 0:
+        raise ValueError("taped moment match supports at most 2048 centres (got %d)" % gp.n)
+    tape = torch.empty(tb // 8, dtype=F64, device=d)
+    g = gp.struct()
+    check(lib.pilco_mm_forward_taped(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(S), ptr(V), ptr(info),
+                                     ptr(ws), wsb, ptr(tape), tb, stream_ptr()), "mm_forward_taped")
+    return M, S, V, info, tape
+
+
+def mm_backward_taped(gp, m, s, M, gM, gS, gV, tape):
+    """pilco_mm_backward_taped -> gm [R,D], gs [R,D,D] from the tape of mm_forward_taped (no recomputation)."""
+    m, s, M, gM, gS, gV = dev(m), dev(s), dev(M), dev(gM), dev(gS), dev(gV)
+    R = m.shape[0]
+    d = device()
+    gm = torch.empty((R, gp.D), dtype=F64, device=d)
+    gs = torch.empty((R, gp.D, gp.D), dtype=F64, device=d)
+    wsb = lib.pilco_mm_tape_bwd_workspace_bytes(gp.D, gp.E, R)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    g = gp.struct()
+    check(lib.pilco_mm_backward_taped(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(gM), ptr(gS), ptr(gV),
+                                      ptr(tape), tape.numel() * 8, ptr(gm), ptr(gs), ptr(ws), wsb, stream_ptr()),
+          "mm_backward_taped")
+    return gm, gs
+
+
 def squash_sin(m, s, max_action):
     m, s, e = dev(m), dev(s), dev(max_action)
     R, U = m.shape
@@ -251,7 +288,9 @@ class RolloutPlan:
     pilco.py:130-134; multiplicative ones form the per-step risk of SafePILCO.predict, safe_pilco.py:29-50, and
     enter the returned reward as ``mult_mu * (1 - prod_t (1 - risk_t))``)."""
 
-    def __init__(self, dyn, policy_spec, reward_terms, m0, S0, H, R=1, mult_mu=0.0):
+    def __init__(self, dyn, policy_spec, reward_terms, m0, S0, H, R=1, mult_mu=0.0, grad=False):
+        """``grad=True``: the forward cascade runs the TAPED dynamics tile pass (pilco_rollout.tape), so that
+        ``backward()`` needs no recomputation; without it ``backward()`` still works (recomputing path)."""
         d = device()
         self.dyn = dyn
         self.R, self.H = int(R), int(H)
@@ -286,10 +325,18 @@ class RolloutPlan:
             ro.rewards[k].W = W.data_ptr()
             ro.rewards[k].t = t.data_ptr() if t is not None else None
         self.m0, self.S0 = dev(m0), dev(S0)
-        bat0 = self.m0.dim() == 2 and self.m0.shape[0] == self.R and self.R > 1
-        self.m0 = self.m0.reshape(-1, self.Ds) if bat0 else self.m0.reshape(self.Ds)
+        # per-restart initial moments: leading dimension R (and R > 1); [1, ...] or unbatched = shared by the batch
+        def _batched(t, tail, what):
+            if t.numel() == int(np.prod(tail)):
+                return False
+            if t.numel() == self.R * int(np.prod(tail)) and t.shape[0] == self.R:
+                return True
+            raise ValueError("%s: expected shape %s or [R=%d, ...], got %s" % (what, tuple(tail), self.R, tuple(t.shape)))
+        bat0 = _batched(self.m0, (self.Ds,), "m0")
+        self.m0 = self.m0.reshape(self.R, self.Ds) if bat0 else self.m0.reshape(self.Ds)
         ro.m0 = self.m0.data_ptr(); ro.m0_bs = self.Ds if bat0 else 0
-        batS = self.S0.dim() == 3
+        batS = _batched(self.S0, (self.Ds, self.Ds), "S0")
+        self.S0 = self.S0.reshape(self.R, self.Ds, self.Ds) if batS else self.S0.reshape(self.Ds, self.Ds)
         ro.S0 = self.S0.data_ptr(); ro.S0_bs = self.Ds * self.Ds if batS else 0
         self.traj_m = torch.empty((self.R, self.H + 1, self.Ds), dtype=F64, device=d)
         self.traj_S = torch.empty((self.R, self.H + 1, self.Ds, self.Ds), dtype=F64, device=d)
@@ -304,6 +351,12 @@ class RolloutPlan:
         wsb = lib.pilco_rollout_workspace_bytes(C.byref(ro))
         self.ws = torch.empty(max(wsb // 8, 2), dtype=F64, device=d)
         ro.ws, ro.ws_bytes = self.ws.data_ptr(), wsb
+        self.tape = None
+        if grad and self.H > 0:
+            tb = lib.pilco_rollout_tape_bytes(C.byref(ro))
+            if tb:                                              # (0: more than 2048 centres -> recomputing backward)
+                self.tape = torch.empty(tb // 8, dtype=F64, device=d)
+                ro.tape, ro.tape_bytes = self.tape.data_ptr(), tb
         self.ro = ro
 
     def forward(self):

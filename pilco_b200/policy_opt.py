@@ -42,7 +42,7 @@ class PolicyEvaluator:
         self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, terms,
                                        np.asarray(pilco.m_init, dtype=np.float64).reshape(-1),
                                        np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=R,
-                                       mult_mu=mult_mu)
+                                       mult_mu=mult_mu, grad=True)
         self.h_flat = torch.empty((R, self.P), dtype=torch.float64).pin_memory()
         self.h_out = torch.empty((R, self.P + 2), dtype=torch.float64).pin_memory()
         self.d_flat = torch.empty((R, self.P), dtype=torch.float64, device=engine.device())

@@ -15,7 +15,7 @@ int main(void) {
     S(pilco_rollout); O(pilco_rollout, dyn); O(pilco_rollout, pol); O(pilco_rollout, n_rewards); O(pilco_rollout, rewards);
     O(pilco_rollout, m0); O(pilco_rollout, S0_bs); O(pilco_rollout, traj_m); O(pilco_rollout, reward);
     O(pilco_rollout, step_reward); O(pilco_rollout, info); O(pilco_rollout, ws); O(pilco_rollout, ws_bytes);
-    O(pilco_rollout, mult_mu); O(pilco_rollout, step_risk);
+    O(pilco_rollout, mult_mu); O(pilco_rollout, step_risk); O(pilco_rollout, tape); O(pilco_rollout, tape_bytes);
     S(pilco_rollout_grad); O(pilco_rollout_grad, gb); O(pilco_rollout_grad, pol_L); O(pilco_rollout_grad, gm0);
     O(pilco_rollout_grad, ws); O(pilco_rollout_grad, ws_bytes);
     printf("version %d\n", PILCO_ABI_VERSION);

@@ -13,7 +13,8 @@ T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
 
 
 @pytest.mark.parametrize("n,D,E,mode,R", [(40, 3, 2, 0, 1), (70, 5, 4, 0, 2), (130, 12, 3, 0, 1), (30, 3, 2, 1, 2),
-                                          (50, 10, 2, 1, 1), (65, 13, 2, 1, 1), (300, 4, 2, 0, 1)])
+                                          (50, 10, 2, 1, 1), (65, 13, 2, 1, 1), (300, 4, 2, 0, 1),
+                                          (600, 3, 2, 0, 1), (600, 5, 2, 1, 1)])      # n > 512: multi-chunk columns
 def test_mm_backward_matches_staged(n, D, E, mode, R):
     from oracle import python_port as pp, staged as st
     from pilco_b200 import engine
@@ -38,6 +39,45 @@ def test_mm_backward_matches_staged(n, D, E, mode, R):
             assert scaled_err(gl[r].cpu().numpy(), rl) < 1e-7, "gell"
 
 
+@pytest.mark.parametrize("n,D,E,mode,R", [(40, 3, 2, 0, 1), (70, 5, 4, 0, 2), (130, 12, 3, 0, 1), (30, 3, 2, 1, 2),
+                                          (300, 4, 2, 0, 1),            # 3 pairs x 1 restart: 4 row splits per pair
+                                          (65, 13, 2, 0, 1), (77, 8, 3, 0, 3),
+                                          (600, 3, 2, 0, 1), (600, 5, 3, 0, 2),      # n > 512: multi-chunk columns
+                                          (300, 12, 10, 0, 2),           # BASELINE metric shape
+                                          (500, 10, 8, 0, 1),            # swimmer
+                                          (400, 7, 6, 0, 1),             # inverted double pendulum
+                                          (200, 12, 10, 0, 1)])          # SMGPR: M = 200 inducing points
+def test_mm_taped_matches_staged(n, D, E, mode, R):
+    """Taped forward + tape-driven reverse sweep (pilco_mm_forward_taped / pilco_mm_backward_taped): forward outputs
+    equal the plain forward's, (gm, gs) equal the numpy statement of the ordered-pair VJP (oracle/staged.py, itself
+    checked against torch autograd) -- including the BASELINE.json shapes."""
+    from oracle import python_port as pp, staged as st
+    from pilco_b200 import engine
+    X, Y, ell, sf2, sn2 = make_gp_problem(n, D, E, seed=n + mode)
+    if mode == 1:
+        sf2, sn2 = np.ones(E), 1e-4 * np.ones(E)
+    gp = engine.gp_factorize(X, Y, ell, sf2, sn2, need_iK=(mode == 0), mode=mode)
+    iK, beta = pp.calculate_factorizations(X, Y, ell, sf2, sn2)
+    rng = np.random.RandomState(5)
+    ms = [make_input(D, seed=20 + r, scale=0.5) for r in range(R)]
+    m = np.concatenate([a for a, _ in ms]); s = np.stack([b for _, b in ms])
+    gM, gS, gV = rng.randn(R, E), rng.randn(R, E, E), rng.randn(R, D, E)
+    M0, S0, V0, _ = engine.mm_forward(gp, m, s)
+    M, S, V, info, tape = engine.mm_forward_taped(gp, m, s)
+    assert int(info.max().item()) == 0
+    for got, ref in ((M, M0), (S, S0), (V, V0)):
+        assert scaled_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-11
+    gm, gs = engine.mm_backward_taped(gp, m, s, M, gM, gS, gV, tape)
+    for r in range(R):
+        rm, rs = st.mm_backward_staged(X, ell, sf2, beta, iK, m[r], s[r], gM[r], gS[r], gV[r], mode)[:2]
+        assert scaled_err(gm[r].cpu().numpy(), rm) < 1e-7, "gm"
+        assert scaled_err(gs[r].cpu().numpy(), rs) < 1e-7, "gs"
+    # ... and the recomputing device VJP gives the same numbers
+    gm2, gs2 = engine.mm_backward(gp, m, s, M, gM, gS, gV)[:2]
+    assert scaled_err(gm.cpu().numpy(), gm2.cpu().numpy()) < 1e-9
+    assert scaled_err(gs.cpu().numpy(), gs2.cpu().numpy()) < 1e-9
+
+
 def _torch_rollout_reward(kind, params, X, Y, ell, sf2, sn2, maxa, Wr, tr, m0, S0, H):
     from oracle import torch_port as tp
     iK, beta = tp.calculate_factorizations(T(X), T(Y), T(ell), T(sf2), T(sn2))
@@ -53,8 +93,9 @@ def _torch_rollout_reward(kind, params, X, Y, ell, sf2, sn2, maxa, Wr, tr, m0, S
     return total[0, 0]
 
 
+@pytest.mark.parametrize("taped", [False, True])
 @pytest.mark.parametrize("kind,R", [("linear", 1), ("linear", 3), ("rbf", 1), ("rbf", 2)])
-def test_rollout_gradient_matches_autograd(kind, R):
+def test_rollout_gradient_matches_autograd(kind, R, taped):
     from pilco_b200 import engine, _lib
     Ds, U, n, H, bf = 3, 2, 50, 4, 12
     D = Ds + U
@@ -73,7 +114,8 @@ def test_rollout_gradient_matches_autograd(kind, R):
         Xc, Yc, lc = rng.randn(R, bf, Ds), 0.1 * rng.randn(R, bf, U), 1.0 + 0.1 * rng.randn(R, U, Ds)
         pgp = engine.gp_factorize(Xc, Yc, lc, np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
         spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pgp)
-    plan = engine.RolloutPlan(gp, spec, rew, m0, S0, H, R=R)
+    plan = engine.RolloutPlan(gp, spec, rew, m0, S0, H, R=R, grad=taped)
+    assert (plan.tape is not None) == taped
     _, _, reward = plan.forward()
     g = plan.backward()
     for r in range(R):
@@ -88,6 +130,43 @@ def test_rollout_gradient_matches_autograd(kind, R):
         for nm, ref in zip(names, grads):
             err = scaled_err(g[nm][r].cpu().numpy(), ref.numpy())
             assert err < 1e-7, "%s grad err %g" % (nm, err)
+
+
+@pytest.mark.parametrize("shape", ["metric", "swimmer"])
+def test_rollout_gradient_at_baseline_shapes(shape):
+    """Policy gradient of the H-step cascade at the BASELINE.json shapes (metric: N=300, D=12, E=10, bf=50;
+    swimmer: N=500, D=10, E=8, bf=40), R=2 restarts: the taped path (what optimize_policy runs) against torch
+    autograd on the reference port, and against the recomputing device path."""
+    from pilco_b200 import engine, _lib
+    from util import make_rollout_problem
+    N, Ds, U, bf, H = (300, 10, 2, 50, 10) if shape == "metric" else (500, 8, 2, 40, 6)
+    R = 2
+    P = make_rollout_problem(N, Ds, U, bf, R, seed=0)
+    gp = engine.gp_factorize(P["X"], P["Y"], P["ell"], P["sf2"], P["sn2"])
+    rew = [dict(kind=_lib.REWARD_EXP, coef=1.0, W=P["W"], t=P["t"])]
+    plans = []
+    for taped in (True, False):
+        pgp = engine.gp_factorize(P["Xc"], P["Yc"], P["lc"], np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
+        spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=P["maxa"], gp=pgp)
+        plan = engine.RolloutPlan(gp, spec, rew, P["m0"], P["S0"], H, R=R, grad=taped)
+        plan.forward()
+        plans.append((plan, {k: v.clone() for k, v in plan.backward().items()}, plan.reward.clone()))
+    (pt, gt, rt), (pr, gr, rr) = plans
+    assert pt.tape is not None and pr.tape is None
+    assert int(pt.info.max().item()) == 0
+    assert scaled_err(rt.cpu().numpy(), rr.cpu().numpy()) < 1e-11
+    for k in ("X", "Y", "ell"):
+        assert scaled_err(gt[k].cpu().numpy(), gr[k].cpu().numpy()) < 1e-8, k
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    for r in range(R):
+        ps = [T(P["Xc"][r]).requires_grad_(), T(P["Yc"][r]).requires_grad_(), T(P["lc"][r]).requires_grad_()]
+        total = _torch_rollout_reward("rbf", ps, P["X"], P["Y"], P["ell"], P["sf2"], P["sn2"], P["maxa"], P["W"], P["t"],
+                                      P["m0"], P["S0"], H)
+        grads = torch.autograd.grad(total, ps)
+        assert abs(float(rt[r]) - float(total.detach())) < 1e-9
+        for nm, ref in zip(("X", "Y", "ell"), grads):
+            err = scaled_err(gt[nm][r].cpu().numpy(), ref.numpy())
+            assert err < 1e-7, "%s grad err %g (%s)" % (nm, err, shape)
 
 
 def test_recipe_cascade_with_policy_optimisation():
@@ -157,7 +236,7 @@ def test_cuda_graph_replay_matches_eager():
     pgp = engine.gp_factorize(Xc, Yc, lc, np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
     spec = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=np.array([2.0]), gp=pgp)
     plan = engine.RolloutPlan(gp, spec, [dict(kind=_lib.REWARD_EXP, coef=1.0, W=np.eye(Ds), t=np.zeros(Ds))],
-                              X[0, :Ds], 0.1 * np.eye(Ds), H, R=R)
+                              X[0, :Ds], 0.1 * np.eye(Ds), H, R=R, grad=True)
     plan.forward(); g0 = {k: v.clone() for k, v in plan.backward().items()}
     r0, m0 = plan.reward.clone(), plan.traj_m.clone()
     plan.capture(backward=True)

@@ -22,7 +22,7 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), "libpilco_b200.so does not export %s" % name
     from pilco_b200 import _lib
     assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert _lib.lib.pilco_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib.pilco_version() == _lib.ABI_VERSION == 3
     assert _lib.lib.pilco_pad_n(300) == 320 and _lib.lib.pilco_pad_n(64) == 64
     assert _lib.lib.pilco_mm_workspace_bytes(300, 12, 10, 2) > 0
     assert _lib.lib.pilco_mm_workspace_bytes(300, 17, 10, 2) == 0          # D > PILCO_MAX_D rejected
@@ -255,7 +255,7 @@ def test_plain_c_caller_links_and_runs(tmp_path):
     env["LD_LIBRARY_PATH"] = "/usr/local/cuda/lib64:" + env.get("LD_LIBRARY_PATH", "")
     out = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
-    assert out.stdout.startswith("abi 2 mm_ws ") and "workspace" in out.stdout
+    assert out.stdout.startswith("abi 3 mm_ws ") and "workspace" in out.stdout
 
 
 def test_table_exp_on_host(tmp_path):

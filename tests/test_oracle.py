@@ -218,3 +218,22 @@ def test_fitc_staged_value_and_gradient(N, M, D):
     rel = lambda a, b: np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(np.asarray(b))) + 1e-300)
     assert rel(g["ell"], gl.numpy()) < 1e-8 and rel(g["Z"], gZ.numpy()) < 1e-8
     assert rel(g["sf2"], gf.numpy()) < 1e-8 and rel(g["sn2"], gn.numpy()) < 1e-8
+
+
+@pytest.mark.parametrize("n,D,E,mode", [(40, 3, 2, 0), (70, 5, 4, 0), (30, 3, 2, 1), (55, 12, 3, 0)])
+def test_tape_formulation_equals_ordered_pair_vjp(n, D, E, mode):
+    """oracle/staged.py: the tape-driven VJP (unordered pairs; row sums, column sums and H Z of every pair -- what the
+    taped device forward leaves behind) gives the same (gm, gs) as the ordered-pair statement that torch autograd pins."""
+    from oracle import staged as st, python_port as pp
+    from util import make_gp_problem, make_input, scaled_err
+    X, Y, ell, sf2, sn2 = make_gp_problem(n, D, E, seed=n + mode)
+    if mode == 1:
+        sf2, sn2 = np.ones(E), 1e-4 * np.ones(E)
+    iK, beta = pp.calculate_factorizations(X, Y, ell, sf2, sn2)
+    m, s = make_input(D, seed=20, scale=0.5)
+    rng = np.random.RandomState(5)
+    gM, gS, gV = rng.randn(E), rng.randn(E, E), rng.randn(D, E)
+    ref = st.mm_backward_staged(X, ell, sf2, beta, iK, m[0], s, gM, gS, gV, mode)
+    tape = st.mm_tape_forward(X, ell, sf2, beta, iK, m[0], s, mode)
+    gm, gs = st.mm_backward_tape(X, ell, sf2, beta, m[0], s, gM, gS, gV, tape)
+    assert scaled_err(gm, ref[0]) < 1e-10 and scaled_err(gs, ref[1]) < 1e-10
