@@ -1,17 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- moment-match rollout steps/s of the B200-native PILCO engine (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--restarts R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config metric|inverted_pendulum|inv_double_pendulum|smgpr|swimmer|test_cascade]
+                    [--restarts R] [--through-api]
 
 One bench "step" = one pass of the hot path over one batch: an H-step moment-matching rollout
 (policy moment match -> squash -> joint -> dynamics moment match -> glue -> reward, pilco.py:118-153)
 for R independent policy restarts per GPU.  value = R*H*N_gpus rollout steps / second.
 
-Workload (metric config, BASELINE.json / SURVEY.md section 8d): N=300 training points, E=Ds=10, U=2, D=12, H=40,
-RBF policy with 50 basis functions, fp64, synthetic seeded data, R=32 restarts per GPU (weak scaling).
+Default workload = the metric config of BASELINE.json: N=300 training points, E=Ds=10, U=2, D=12,
+H=40, RBF policy with 50 basis functions, fp64, synthetic seeded data, R=32 restarts per GPU (weak scaling).
+`--config` selects one of BASELINE.json's `configs` shapes instead (same JSON line, its own roofline / CPU leg).
+`--through-api` (any config) drives `PILCO.optimize_policy(restarts=R*N)` itself -- lock-step L-BFGS-B,
+taped forward + reverse sweep per evaluation, one all_gather of [loss | params] -- and reports wall-clock
+loss-evaluations x R x H / s.
 
 Rank 0 prints ONE JSON line.  `--impl reference` times the reference-equivalent CPU path
-(oracle/torch_port.py, all host threads) on a bounded sample of the same workload.
+(oracle/torch_port.py, all host threads it can use) on bounded samples of the same workload.
 """
 import argparse
 import ctypes as C
@@ -30,16 +36,37 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"
 
-CFG = dict(N=300, Ds=10, U=2, H=40, bf=50)
-METRIC = "moment-match rollout steps/sec (N=300, E=10, H=40, fp64)"
+# BASELINE.json `configs` as code-derived shapes: E = Ds, D = Ds + U.  R = restarts per GPU.
+CONFIGS = {
+    "metric": dict(N=300, Ds=10, U=2, bf=50, H=40, R=32, S0=0.1,
+                   name="metric config: N=300 E=Ds=10 U=2 D=12 H=40, RBF policy bf=50"),
+    "test_cascade": dict(N=100, Ds=2, U=1, bf=0, H=30, R=1, S0=0.1,
+                         name="test_cascade.py: N=100 D=3 E=2 H=30, linear policy, single restart"),
+    "inverted_pendulum": dict(N=300, Ds=4, U=1, bf=10, H=40, R=1, S0=0.1,
+                              name="inverted_pendulum.py: N=300 E=4 D=5 H=40, RBF bf=10, single restart"),
+    "inv_double_pendulum": dict(N=400, Ds=6, U=1, bf=40, H=40, R=32, S0=0.1,
+                                name="inv_double_pendulum.py: N=400 E=6 D=7 H=40, RBF bf=40, 32 restarts batched"),
+    "smgpr": dict(N=2000, M=200, Ds=10, U=2, bf=50, H=40, R=32, S0=0.1,
+                  name="SMGPR sparse path: N=2000 M=200 E=10 D=12 H=40, RBF bf=50"),
+    "swimmer": dict(N=500, Ds=8, U=2, bf=40, H=50, R=32, S0=0.005,
+                    name="swimmer.py: N=500 E=8 D=10 H=50, RBF bf=40, 256 restarts over 8 GPUs (32 per GPU)"),
+}
 UNIT = "rollout-steps/s"
 EXP_FLOP_EQ = 14.0          # fp64 flop-equivalents of one exp: exp_shifted()'s 7 fp64-pipe instructions (3 DADD, 3 DFMA, DMUL), 2 each
 
 
-def make_workload(seed=0, R=32):
-    """Seeded synthetic problem (SURVEY.md 8d recipe).  Restart r uses RandomState(seed+1+r) so any
-    sharding over ranks produces the same per-restart policies."""
-    N, Ds, U, bf = CFG["N"], CFG["Ds"], CFG["U"], CFG["bf"]
+def metric_name(cfg):
+    if cfg is CONFIGS["metric"]:
+        return "moment-match rollout steps/sec (N=300, E=10, H=40, fp64)"
+    n = ("M=%d of N=%d" % (cfg["M"], cfg["N"])) if "M" in cfg else "N=%d" % cfg["N"]
+    return "moment-match rollout steps/sec (%s, E=%d, H=%d, fp64)" % (n, cfg["Ds"], cfg["H"])
+
+
+def make_workload(cfg, seed=0):
+    """Seeded synthetic problem (SURVEY.md section 8d recipe; deviations documented in BASELINE.md section 6: state differences
+    and signal variances scaled by 0.05, noise 1e-3, so that a 40-50 step rollout with UNTRAINED hyper-parameters stays
+    finite).  Restart r uses RandomState(seed+1+r), so any sharding over ranks sees the same per-restart policies."""
+    N, Ds, U = cfg["N"], cfg["Ds"], cfg["U"]
     D = Ds + U
     rng = np.random.RandomState(seed)
     X = rng.rand(N, D)
@@ -48,22 +75,45 @@ def make_workload(seed=0, R=32):
     ell = 1.0 + rng.rand(Ds, D)
     sf2 = 0.05 * (1.0 + rng.rand(Ds))
     sn2 = 1e-3 * np.ones(Ds)
-    m0 = X[0, :Ds].copy()
-    S0 = 0.1 * np.eye(Ds)
-    W = np.eye(Ds)
-    t = np.zeros(Ds)
-    return dict(X=X, Y=Y, ell=ell, sf2=sf2, sn2=sn2, m0=m0, S0=S0, W=W, t=t)
+    wl = dict(X=X, Y=Y, ell=ell, sf2=sf2, sn2=sn2, m0=X[0, :Ds].copy(), S0=cfg["S0"] * np.eye(Ds), W=np.eye(Ds), t=np.zeros(Ds))
+    if "M" in cfg:
+        wl["Z"] = np.random.RandomState(seed + 7).rand(cfg["M"], D)        # smgpr.py:20
+    return wl
 
 
-def make_policies(restart_ids, seed=0):
-    Ds, U, bf = CFG["Ds"], CFG["U"], CFG["bf"]
+def make_policies(cfg, restart_ids, seed=0):
+    Ds, U, bf = cfg["Ds"], cfg["U"], cfg["bf"]
+    if bf == 0:                                                             # linear policy (test_cascade.py)
+        Ws, bs = [], []
+        for r in restart_ids:
+            rng = np.random.RandomState(seed + 1 + int(r))
+            Ws.append(rng.rand(U, Ds)); bs.append(rng.rand(U))
+        return dict(W=np.stack(Ws), b=np.stack(bs))
     Xc, Yc, lc = [], [], []
     for r in restart_ids:
         rng = np.random.RandomState(seed + 1 + int(r))
         Xc.append(rng.randn(bf, Ds) * 0.5 + 0.5)
         Yc.append(0.1 * rng.randn(bf, U))
         lc.append(1.0 + 0.1 * rng.randn(U, Ds))
-    return np.stack(Xc), np.stack(Yc), np.stack(lc)
+    return dict(Xc=np.stack(Xc), Yc=np.stack(Yc), lc=np.stack(lc))
+
+
+def step_counts(cfg):
+    """SURVEY.md section 8d / BASELINE.md section 5: algorithmic flops, exps and compulsory bytes of ONE rollout step
+    (dynamics call over n centres + policy call over bf centres)."""
+    def mm(n, D, E, trace):
+        P = E * (E + 1) // 2
+        F = P * (2 * n * n * D + 2 * n * D * D) + 4 * P * n * n + (2 * E * n * n if trace else 0) + E * (2 * n * D * D + 6 * n * D)
+        Xe = P * n * n + E * n
+        B = 8 * (n * D + E * n + (E * n * n if trace else 0) + 2 * E * D + D * D + D + E + E * E + D * E)
+        return F, Xe, B
+    n = cfg.get("M", cfg["N"])
+    Ds, U, bf = cfg["Ds"], cfg["U"], cfg["bf"]
+    F, Xe, B = mm(n, Ds + U, Ds, True)
+    if bf:
+        F2, X2, B2 = mm(bf, Ds, U, False)
+        F, Xe, B = F + F2, Xe + X2, B + B2
+    return F, Xe, B
 
 
 # ------------------------------------------------------------------------------------------------
@@ -89,7 +139,7 @@ def pick_cpu_threads():
         torch.exp(x)                                  # warm the pool
         t0 = time.perf_counter()
         for _ in range(3):
-            y = torch.exp(x + 1.0) @ x[0, 0]
+            y = torch.exp(x + 1.0) @ x[0, 0]          # noqa: F841
         dt = time.perf_counter() - t0
         if dt < best_t * 0.9:                         # prefer fewer threads unless clearly faster
             best, best_t = c, dt
@@ -97,35 +147,62 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_reference_steps_per_s(wl, reps=2, h_sample=4, threads=None):
-    import torch
-    from oracle import torch_port as tp
-    threads = threads or pick_cpu_threads()
-    torch.set_num_threads(threads)
-    T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
-    X, Y, ell, sf2, sn2 = map(T, (wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"]))
-    Xc, Yc, lc = make_policies([0])
-    Xc, Yc, lc = T(Xc[0]), T(Yc[0]), T(lc[0])
-    maxa = torch.ones((1, CFG["U"]), dtype=torch.float64)
-    W, t = T(wl["W"]), T(wl["t"])[None]
-    Ds = CFG["Ds"]
+class CpuRollout:
+    """The reference-equivalent CPU path (oracle/torch_port.py) for restart 0 of a config: one rollout of
+    ``h`` steps, factorisations recomputed inside every step as the reference does (mgpr.py:77-79, smgpr.py,
+    controllers.py:115); ``grad=True`` also runs torch autograd back to the policy parameters (what
+    gpflow.optimizers.Scipy differentiates, pilco.py:84-90)."""
 
-    def one_rollout():
-        # the reference recomputes both factorisations inside every step (mgpr.py:77-79, controllers.py:115)
+    def __init__(self, cfg, wl, threads=None):
+        import torch
+        from oracle import torch_port as tp
+        self.torch, self.tp, self.cfg, self.wl = torch, tp, cfg, wl
+        self.threads = threads or pick_cpu_threads()
+        torch.set_num_threads(self.threads)
+        T = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)
+        self.T = T
+        self.X, self.Y, self.ell, self.sf2, self.sn2 = map(T, (wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"]))
+        self.Z = T(wl["Z"]) if "Z" in wl else None
+        pol = make_policies(cfg, [0])
+        self.pol = {k: T(v[0]) for k, v in pol.items()}
+        self.maxa = torch.ones((1, cfg["U"]), dtype=torch.float64)
+        self.W, self.t = T(wl["W"]), T(wl["t"])[None]
+
+    def run(self, h, grad=False):
+        torch, tp = self.torch, self.tp
+        ps = {k: v.clone().requires_grad_(grad) for k, v in self.pol.items()}
+
         def dyn(m, s):
-            iK, beta = tp.calculate_factorizations(X, Y, ell, sf2, sn2)
-            return tp.predict_given_factorizations(X, ell, sf2, m, s, iK, beta)
-        act = lambda m, s: tp.rbf_action(Xc, Yc, lc, m, s, maxa)
-        rew = lambda m, s: tp.exponential_reward(m, s, W, t)
-        with torch.no_grad():
-            return tp.predict(T(wl["m0"])[None], T(wl["S0"]), h_sample, act, dyn, rew)
+            if self.Z is not None:
+                iK, beta = tp.fitc_factorizations(self.X, self.Z, self.Y, self.ell, self.sf2, self.sn2)
+                return tp.predict_given_factorizations(self.Z, self.ell, self.sf2, m, s, iK, beta)
+            iK, beta = tp.calculate_factorizations(self.X, self.Y, self.ell, self.sf2, self.sn2)
+            return tp.predict_given_factorizations(self.X, self.ell, self.sf2, m, s, iK, beta)
+        if "W" in ps:
+            act = lambda m, s: tp.linear_action(ps["W"], ps["b"][None], m, s, self.maxa)
+        else:
+            act = lambda m, s: tp.rbf_action(ps["Xc"], ps["Yc"], ps["lc"], m, s, self.maxa)
+        rew = lambda m, s: tp.exponential_reward(m, s, self.W, self.t)
+        ctx = torch.enable_grad() if grad else torch.no_grad()
+        with ctx:
+            _, _, total = tp.predict(self.T(self.wl["m0"])[None], self.T(self.wl["S0"]), h, act, dyn, rew)
+            if grad:
+                total[0, 0].backward()
+        return float(total.detach())
 
-    one_rollout()                       # warm-up
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        one_rollout()
-    dt = time.perf_counter() - t0
-    return reps * h_sample / dt, threads, "R=1, %d rollouts of %d steps (of H=%d), factorisations recomputed per step as in the reference" % (reps, h_sample, CFG["H"])
+    def steps_per_s(self, reps=2, h=4, grad=False, budget_s=30.0):
+        self.run(1, grad)                                   # warm-up
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(reps):
+            self.run(h, grad)
+            done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = time.perf_counter() - t0
+        what = "forward+backward (torch autograd)" if grad else "forward"
+        return done * h / dt, "R=1, %d rollouts of %d steps (of H=%d), %s, factorisations recomputed per step as in the reference" % (
+            done, h, self.cfg["H"], what)
 
 
 _REAL_REF_SCRIPT = r"""
@@ -154,19 +231,19 @@ print(json.dumps({"steps_per_s": reps * h / (time.perf_counter() - t0)}))
 """
 
 
-def real_reference_steps_per_s(wl, reps=2, h_sample=4):
+def real_reference_steps_per_s(cfg, wl, reps=2, h_sample=4):
     """if a reference install ever appears under baseline/_ref (TensorFlow + GPflow + the reference's
     own ``pilco`` package), time the UNMODIFIED reference through its public API (PILCO.predict, pilco.py:118-136)
     in a separate interpreter (its package name collides with this repo's alias package).  Returns None when it is
     not there or does not import -- the normal case: nothing in /opt/wheelhouse provides tensorflow or gpflow."""
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref_dir, "pilco")):
+    if not os.path.isdir(os.path.join(ref_dir, "pilco")) or cfg["bf"] == 0 or "M" in cfg:
         return None
     import tempfile
     try:
-        Xc, Yc, lc = make_policies([0])
+        pol = make_policies(cfg, [0])
         with tempfile.TemporaryDirectory() as td:
-            np.savez(os.path.join(td, "wl.npz"), Xc=Xc[0], Yc=Yc[0], lc=lc[0], **wl)
+            np.savez(os.path.join(td, "wl.npz"), Xc=pol["Xc"][0], Yc=pol["Yc"][0], lc=pol["lc"][0], **wl)
             open(os.path.join(td, "run.py"), "w").write(_REAL_REF_SCRIPT)
             env = dict(os.environ, PYTHONPATH=ref_dir)
             out = subprocess.run([sys.executable, os.path.join(td, "run.py"), os.path.join(td, "wl.npz"), str(h_sample), str(reps)],
@@ -178,29 +255,49 @@ def real_reference_steps_per_s(wl, reps=2, h_sample=4):
         return None
 
 
-def run_reference(args):
+def workload_string(cfg, R):
+    return "%s, R=%d restarts/GPU, forward rollout" % (cfg["name"], R)
+
+
+def run_reference(args, cfg):
+    """`--impl reference`: each bench step = ONE bounded sample of the workload (restart 0, the first `h` of the H
+    rollout steps) through the reference-equivalent CPU path; W untimed + K timed samples; `steps`/`ms_per_step` are
+    the real ones of this run (the run is cut after two minutes, `steps` then says how many samples were timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = make_workload()
-    # warm-up / steps map onto repetitions of a bounded sample
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_steps_per_s(wl, reps=1, h_sample=2)
+    wl = make_workload(cfg)
+    h = 4 if cfg.get("M", cfg["N"]) >= 200 else min(cfg["H"], 10)
+    cpu = CpuRollout(cfg, wl)
+    nwarm = max(1, min(args.warmup, 2))
+    for _ in range(nwarm):
+        cpu.run(h)
+    K = max(1, args.steps)
     t0 = time.perf_counter()
-    v, cores, sample = cpu_reference_steps_per_s(wl, reps=max(1, min(args.steps, 3)), h_sample=4)
+    done = 0
+    for _ in range(K):
+        cpu.run(h)
+        done += 1
+        if time.perf_counter() - t0 > 120.0:              # bounded: never let the CPU arm run past two minutes
+            break
     dt = time.perf_counter() - t0
+    v = done * h / dt
     kind, note = "port", "reference-equivalent CPU restatement (oracle/torch_port.py); TensorFlow/GPflow are not installable offline"
-    real = real_reference_steps_per_s(wl, reps=max(1, min(args.steps, 3)), h_sample=4)
+    sample = "each step = restart 0, first %d of H=%d rollout steps, forward, factorisations recomputed per step as in the reference" % (h, cfg["H"])
+    cores = cpu.threads
+    real = real_reference_steps_per_s(cfg, wl, reps=max(1, min(done, 3)), h_sample=h)
     if real is not None:
         v, cores, kind = real, os.cpu_count() or 1, "reference"
         note = "the unmodified reference from baseline/_ref through PILCO.predict (TensorFlow/GPflow on the host cores)"
+    R = args.restarts or cfg["R"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v * CFG["H"], "higher_is_better": True,
+        "impl": "reference", "metric": metric_name(cfg), "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": done, "warmup": nwarm, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "metric config N=300 E=10 D=12 H=40 RBF bf=50 (CPU sample: R=1)"},
+        "config": {"workload": workload_string(cfg, R), "restarts_per_gpu": R},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rollout_steps_per_bench_step": h, "host_cpus": os.cpu_count(),
         "note": note,
     }
     print(json.dumps(line))
@@ -240,11 +337,86 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons)}
 
 
-def run_ours(args):
+def build_pilco(cfg, wl, pol):
+    """The workload as the reference's own objects (drop-in class API): PILCO + RbfController/LinearController +
+    ExponentialReward with the synthetic hyper-parameters assigned (no training)."""
+    from pilco.models import PILCO
+    from pilco.controllers import RbfController, LinearController
+    from pilco.rewards import ExponentialReward
+    Ds, U = cfg["Ds"], cfg["U"]
+    np.random.seed(0)
+    if cfg["bf"]:
+        ctrl = RbfController(Ds, U, cfg["bf"], max_action=1.0)
+        ctrl.set_data((pol["Xc"][0], pol["Yc"][0]))
+        for i, m in enumerate(ctrl.models):
+            m.kernel.lengthscales.assign(pol["lc"][0][i])
+    else:
+        ctrl = LinearController(Ds, U, max_action=1.0)
+        ctrl.W.assign(pol["W"][0]); ctrl.b.assign(pol["b"][0][None])
+    kw = dict(num_induced_points=cfg["M"]) if "M" in cfg else {}
+    p = PILCO((wl["X"], wl["Y"]), controller=ctrl, horizon=cfg["H"], reward=ExponentialReward(Ds, W=wl["W"], t=wl["t"]),
+              m_init=wl["m0"][None], S_init=wl["S0"], **kw)
+    for i, m in enumerate(p.mgpr.models):
+        m.kernel.lengthscales.assign(wl["ell"][i]); m.kernel.variance.assign(wl["sf2"][i]); m.likelihood.variance.assign(wl["sn2"][i])
+        if "M" in cfg:
+            m.inducing_variable.Z.assign(wl["Z"])
+    return p
+
+
+def run_through_api(args, cfg):
+    """`--through-api`: PILCO.optimize_policy(restarts = R x world) under torchrun -- the real sharded path: restart
+    r on rank r % world, lock-step SciPy L-BFGS-B, every evaluation one captured graph (policy factorisation, taped
+    H-step forward, reverse sweep), ONE all_gather of [loss | params] at the end (NCCL)."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl")
+    from pilco_b200 import policy_opt
+    R = args.restarts or cfg["R"]
+    wl = make_workload(cfg)
+    p = build_pilco(cfg, wl, make_policies(cfg, [0]))
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):                 # (randomize() / optimize_policy() print per restart)
+        p.optimize_policy(maxiter=2, restarts=R * world)   # warm-up: builds the evaluator, captures its graph
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        reward = p.optimize_policy(maxiter=args.maxiter, restarts=R * world)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    st = dict(policy_opt.LAST_STATS)
+    tt = torch.tensor([dt, float(st["evals"] * st["restarts_local"] * st["horizon"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, steps = float(tmax[0]), float(tsum[1])
+    else:
+        steps = float(tt[1])
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric_name(cfg) + " through PILCO.optimize_policy", "value": steps / dt, "unit": UNIT, "n_gpus": world,
+            "steps": args.maxiter, "warmup": 2, "ms_per_step": 1e3 * dt / max(st["evals"], 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s; PILCO.optimize_policy(maxiter=%d, restarts=%d): lock-step L-BFGS-B, forward + reverse sweep per evaluation, wall clock incl. SciPy and host<->device copies"
+                                   % (cfg["name"], args.maxiter, R * world), "restarts_per_gpu": R},
+            "loss_evaluations": st["evals"], "wall_s": dt, "best_reward": float(reward),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     from pilco_b200 import engine, _lib
     from pilco_b200._lib import lib
+    from pilco_b200.engine import ptr, stream_ptr
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,31 +425,49 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl")
     d = engine.device()
-    R, H = args.restarts, CFG["H"]
-    Ds, U, bf, N = CFG["Ds"], CFG["U"], CFG["bf"], CFG["N"]
+    R, H = args.restarts or cfg["R"], cfg["H"]
+    Ds, U, bf = cfg["Ds"], cfg["U"], cfg["bf"]
     D = Ds + U
-    wl = make_workload()
-    gp = engine.gp_factorize(wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"])      # once per set_data
-    my_ids = np.arange(rank * R, (rank + 1) * R)                                     # weak scaling: R per GPU
-    Xc, Yc, lc = make_policies(my_ids)
+    wl = make_workload(cfg)
+
+    def timeit(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    if "M" in cfg:                                          # FITC over M inducing points (once per set_data / hyper change)
+        gp = engine.fitc_factorize(wl["X"], wl["Z"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"])
+        fact_ms = timeit(lambda: engine.fitc_factorize(wl["X"], wl["Z"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"]))
+    else:
+        gp = engine.gp_factorize(wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"])      # once per set_data
+        fact_ms = timeit(lambda: engine.gp_refactorize(gp))
+    n_c = gp.n                                              # centres of the moment match (N, or M for SMGPR)
+    my_ids = np.arange(rank * R, (rank + 1) * R)            # weak scaling: R per GPU
+    pol = make_policies(cfg, my_ids)
     ones, noise = np.ones((R, U)), 1e-4 * np.ones((R, U))
     maxa = np.ones(U)
     rew = [dict(kind=_lib.REWARD_EXP, coef=1.0, W=wl["W"], t=wl["t"])]
+    nsplit = max(1, min(args.nsplit, R))
+
+    def policy_spec(lo, hi, store):
+        if bf == 0:
+            return dict(kind=_lib.POLICY_LINEAR, Ds=Ds, U=U, squash=True, max_action=maxa, W=pol["W"][lo:hi], b=pol["b"][lo:hi])
+        pg = engine.gp_factorize(pol["Xc"][lo:hi], pol["Yc"][lo:hi], pol["lc"][lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
+        store[(lo, hi)] = pg
+        return dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
 
     # ---- device-resident arm: policy parameters already in HBM, rollout only --------------------------
     # The H-step loop of all R restarts is ONE CUDA graph: nsplit sub-batches on parallel streams (their
-    # latency-bound per-step kernels overlap each other's tile kernels), 6H+1 kernel nodes per sub-batch.
-    nsplit = max(1, min(args.nsplit, R))
+    # latency-bound per-step kernels overlap each other's tile kernels).
     pgps = {}
 
     def make_plan(lo, hi, grad=False):
-        pg = engine.gp_factorize(Xc[lo:hi], Yc[lo:hi], lc[lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
-        pgps[(lo, hi)] = pg
-        sp = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
-        return engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo, grad=grad)
+        return engine.RolloutPlan(gp, policy_spec(lo, hi, pgps), rew, wl["m0"], wl["S0"], H, R=hi - lo, grad=grad)
 
     split = engine.SplitRollout(make_plan, R, nsplit=nsplit)
-    plan = split.plans[0]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=d)       # > L2 (126 MB)
     gathered = [torch.empty(R, dtype=torch.float64, device=d) for _ in range(world)]
 
@@ -290,27 +480,37 @@ def run_ours(args):
     # What one optimiser evaluation does through the public engine objects: pinned host policy parameters ->
     # device, policy factorisation (beta = (K+sn2 I)^-1 Y, pilco_gp_factorize), H-step rollout, rewards -> host.
     # Device work is one captured CUDA graph (refactorise + cascade, same sub-batch split) replayed per step.
-    hX = torch.as_tensor(Xc).pin_memory(); hY = torch.as_tensor(Yc).pin_memory(); hl = torch.as_tensor(lc).pin_memory()
+    keys = ("W", "b") if bf == 0 else ("Xc", "Yc", "lc")
+    hbuf = {k: torch.as_tensor(pol[k]).pin_memory() for k in keys}
     h_out = torch.empty(R, dtype=torch.float64).pin_memory()
-    h2d = (hX.numel() + hY.numel() + hl.numel()) * 8
+    h2d = sum(v.numel() for v in hbuf.values()) * 8
     d2h = R * 8
-    pg2 = {}
 
-    def make_plan2(lo, hi):
-        pg = engine.gp_factorize(Xc[lo:hi], Yc[lo:hi], lc[lo:hi], ones[lo:hi], noise[lo:hi], need_iK=False, mode=1)
-        pg2[(lo, hi)] = pg
-        sp = dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True, max_action=maxa, gp=pg)
-        pl = engine.RolloutPlan(gp, sp, rew, wl["m0"], wl["S0"], H, R=hi - lo)
-        fwd = pl.forward
-        pl.forward = lambda: (engine.gp_refactorize(pg), fwd())[1]      # refactorise inside the captured graph
-        return pl
+    def plan_factory(pgs, plans, grad):
+        def make(lo, hi):
+            pl = engine.RolloutPlan(gp, policy_spec(lo, hi, pgs), rew, wl["m0"], wl["S0"], H, R=hi - lo, grad=grad)
+            plans[(lo, hi)] = pl
+            if bf:
+                pg = pgs[(lo, hi)]
+                fwd = pl.forward
+                pl.forward = lambda: (engine.gp_refactorize(pg), fwd())[1]      # refactorise inside the captured graph
+            return pl
+        return make
 
-    split2 = engine.SplitRollout(make_plan2, R, nsplit=nsplit)
+    pg2, plans2 = {}, {}
+    split2 = engine.SplitRollout(plan_factory(pg2, plans2, False), R, nsplit=nsplit)
+
+    def upload(plans, pgs):
+        for (lo, hi), pl in plans.items():
+            if bf == 0:
+                pl.W.copy_(hbuf["W"][lo:hi], non_blocking=True); pl.b.copy_(hbuf["b"][lo:hi], non_blocking=True)
+            else:
+                pg = pgs[(lo, hi)]
+                pg.X.copy_(hbuf["Xc"][lo:hi], non_blocking=True); pg.Y.copy_(hbuf["Yc"][lo:hi], non_blocking=True)
+                pg.ell.copy_(hbuf["lc"][lo:hi], non_blocking=True)
 
     def step_e2e():
-        for (lo, hi), pg in pg2.items():
-            pg.X.copy_(hX[lo:hi], non_blocking=True); pg.Y.copy_(hY[lo:hi], non_blocking=True)
-            pg.ell.copy_(hl[lo:hi], non_blocking=True)
+        upload(plans2, pg2)
         rw = split2.replay()
         h_out.copy_(rw, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -339,11 +539,31 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)           # max over ranks
         return float(t.item()) / K                             # ms per step
 
-    # ---- forward + reverse sweep (policy gradient), device resident: extra line, not the headline -----------
-    split3 = engine.SplitRollout(lambda lo, hi: make_plan(lo, hi, grad=True), R, nsplit=nsplit, backward=True) if args.with_backward else None
+    # ---- forward + reverse sweep (policy gradient): the loop optimize_policy runs ------------------------
+    # taped forward (pilco_rollout.tape) + tape-driven reverse sweep; device resident and end to end
+    # (host parameters in, [reward | gradient] out), one captured graph each
+    split3 = split4 = None
+    if args.with_backward:
+        split3 = engine.SplitRollout(lambda lo, hi: make_plan(lo, hi, grad=True), R, nsplit=nsplit, backward=True)
+        pg4, plans4 = {}, {}
+        split4 = engine.SplitRollout(plan_factory(pg4, plans4, True), R, nsplit=nsplit, backward=True)
+        gkeys = ("W", "b") if bf == 0 else ("X", "Y", "ell")
+        first = plans4[next(iter(plans4))]
+        gsz = sum(int(np.prod(first.gbuf[k].shape[1:])) for k in gkeys)
+        h_grad = torch.empty((R, 1 + gsz), dtype=torch.float64).pin_memory()
+        d_grad = torch.empty((R, 1 + gsz), dtype=torch.float64, device=d)
 
     def step_fwd_bwd():
         split3.replay()
+
+    def step_fwd_bwd_e2e():
+        upload(plans4, pg4)
+        rw = split4.replay()
+        d_grad[:, 0] = rw
+        for (lo, hi), pl in plans4.items():
+            d_grad[lo:hi, 1:] = torch.cat([pl.gbuf[k].reshape(hi - lo, -1) for k in gkeys], dim=1)
+        h_grad.copy_(d_grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -351,7 +571,11 @@ def run_ours(args):
     ms_res = timed(step_resident, args.steps, args.warmup)
     ok = int(split.info.max().item()) == 0 and bool(torch.isfinite(split.reward).all().item())
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
-    ms_fb = timed(step_fwd_bwd, max(3, args.steps // 2), 2) if split3 is not None else None
+    ms_fb = ms_fb_e2e = None
+    if split3 is not None:
+        kb = max(3, args.steps // 2)
+        ms_fb = timed(step_fwd_bwd, kb, 3)
+        ms_fb_e2e = timed(step_fwd_bwd_e2e, kb, 3)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -365,89 +589,163 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (dynamics mm_tile) -------------------------------------------
+    # ---- class-API line: PILCO.predict(m, S, H) with host arrays in / out (one restart, the reference's call) ----
+    api = None
+    if args.api_line:
+        try:
+            p = build_pilco(cfg, wl, make_policies(cfg, [0]))
+            p.predict(wl["m0"][None], wl["S0"], H)             # builds + captures the cached plan
+            reps = 20
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                p.predict(wl["m0"][None], wl["S0"], H)
+            dt = (time.perf_counter() - t0) / reps
+            api = {"call": "pilco.models.PILCO.predict(m, S, %d) -- numpy in, numpy out, R=1" % H, "ms_per_call": 1e3 * dt,
+                   "value": H / dt, "unit": UNIT, "us_per_rollout_step": 1e6 * dt / H}
+        except Exception as exc:                               # pragma: no cover
+            api = {"error": repr(exc)}
+
+    # ---- roofline of the dominant kernel (dynamics tile kernel: plain forward, and taped) ----------------------
     ms3 = (C.c_float * 3)()
-    from pilco_b200.engine import ptr, stream_ptr
     g = gp.struct()
     E = Ds
     Mo = torch.empty((R, E), dtype=torch.float64, device=d); So = torch.empty((R, E, E), dtype=torch.float64, device=d)
     Vo = torch.empty((R, D, E), dtype=torch.float64, device=d); info = torch.zeros(R, dtype=torch.int32, device=d)
-    wsb = lib.pilco_mm_workspace_bytes(N, D, E, R)
+    wsb = lib.pilco_mm_workspace_bytes(n_c, D, E, R)
     ws = torch.empty(wsb // 8, dtype=torch.float64, device=d)
+    tb = lib.pilco_mm_tape_bytes(n_c, D, E, R)
+    tape = torch.empty(max(tb // 8, 2), dtype=torch.float64, device=d)
     mj = engine.dev(np.tile(np.concatenate([wl["m0"], np.zeros(U)]), (R, 1)))
     sj = engine.dev(np.tile(0.1 * np.eye(D), (R, 1, 1)))
-    tile_ms, setup_ms = [], []
+    tile_ms, setup_ms, ttile_ms = [], [], []
     for i in range(8):
         flush.fill_(1.0)
         _lib.check(lib.pilco_mm_forward_profile(C.byref(g), R, ptr(mj), ptr(sj), ptr(Mo), ptr(So), ptr(Vo), ptr(info),
                                                 ptr(ws), wsb, ms3, stream_ptr()))
         if i >= 3:
             setup_ms.append(ms3[0]); tile_ms.append(ms3[1])
+        if tb:
+            flush.fill_(1.0)
+            _lib.check(lib.pilco_mm_forward_taped_profile(C.byref(g), R, ptr(mj), ptr(sj), ptr(Mo), ptr(So), ptr(Vo), ptr(info),
+                                                          ptr(ws), wsb, ptr(tape), tb, ms3, stream_ptr()))
+            if i >= 3:
+                ttile_ms.append(ms3[1])
     tile_ms = float(np.mean(tile_ms)); setup_ms = float(np.mean(setup_ms))
-    # fp64 pipe peaks measured live (DFMA and DMMA microbenchmarks, same process)
+    ttile_ms = float(np.mean(ttile_ms)) if ttile_ms else None
+    # fp64 pipe peaks measured live (DFMA and DMMA microbenchmarks, same process): 8 DMMA.8x8x4 per warp and iteration,
+    # 256 FMA = 512 flop each
     sink = torch.zeros(8, dtype=torch.float64, device=d)
     msf = C.c_float()
     iters, blocks = 20000, 148 * 4
     _lib.check(lib.pilco_microbench_fp64(0, iters, blocks, ptr(sink), C.byref(msf), stream_ptr()))
     dfma_tf = 2 * blocks * 256 * iters * 8.0 / (msf.value * 1e-3) / 1e12
     _lib.check(lib.pilco_microbench_fp64(1, iters, blocks, ptr(sink), C.byref(msf), stream_ptr()))
-    dmma_tf = 2 * blocks * 8 * iters * 16.0 * 256 / (msf.value * 1e-3) / 1e12
+    dmma_tf = blocks * 8 * iters * 8.0 * 512 / (msf.value * 1e-3) / 1e12
+    # independent library denominator (NOT on the product path): cuBLAS DGEMM through torch.matmul
+    lib_tf, nmm = None, 6144
+    try:
+        a_ = torch.randn(nmm, nmm, dtype=torch.float64, device=d); b_ = torch.randn(nmm, nmm, dtype=torch.float64, device=d)
+        torch.matmul(a_, b_); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a_, b_); torch.matmul(a_, b_); e1.record(); torch.cuda.synchronize()
+        lib_tf = 2 * 2.0 * nmm ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        del a_, b_
+    except Exception:
+        pass
     P = E * (E + 1) // 2
-    # algorithmic pair-elements per launch: symmetric (a == a) pairs need only half of their n x n elements
-    elems = (float(P) - 0.5 * E) * N * N * R
-    dot_flops = 2.0 * D * elems                                    # Q-contraction U'.zeta (DMMA)
-    other_flops = (2.0 + EXP_FLOP_EQ) * elems + 2.0 * (0.5 * E * N * N * R)   # exp, beta-weighted sum (A'+B ride in the DMMA C operand / rounding constant); trace term
-    flops = dot_flops + other_flops
-    achieved = flops / (tile_ms * 1e-3) / 1e12
-    peak_eff = flops / (dot_flops / dmma_tf + other_flops / dfma_tf)   # time-weighted fp64 peak for this kernel's op mix
-    # compulsory bytes per launch: iK once (shared, L2 resident) + per restart zeta, beta, B_q and the per-pair blocks
-    npad, ks = (N + 63) // 64 * 64, (D + 3) // 4
-    # ... and the row-side operands materialised by setup stage 2 (U' fragments 4*ks doubles + A' per pair and row)
-    alg_bytes = 8.0 * (E * N * N + R * (N * D + E * N + P * N + P * 552 + P * npad * (4 * ks + 1)))
+    nn = float(n_c) * n_c
+    ks = (D + 3) // 4
+
+    def tile_block(ms, elems, dmma_extra, dfma_extra, label, trace_elems):
+        dot = 2.0 * D * elems                                  # Q-contraction U'.zeta (DMMA)
+        hz = dmma_extra * elems                                # second product H.[Z,1] (taped only, DMMA)
+        other = (EXP_FLOP_EQ + dfma_extra) * elems + 2.0 * trace_elems
+        flops = dot + hz + other
+        ach = flops / (ms * 1e-3) / 1e12
+        peak = flops / ((dot + hz) / dmma_tf + other / dfma_tf)   # time-weighted fp64 peak for this kernel's op mix
+        return {"kernel": label, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "tensor_flops_share": (dot + hz) / flops, "q_contraction_tflops": dot / (ms * 1e-3) / 1e12, "kernel_ms": ms}
+    # plain forward: symmetric (a == a) pairs need only half of their n x n elements; A'+B ride in the DMMA C operand /
+    # rounding constant, so per element: the dot, one exp, one weighted add (+ trace term on diagonal pairs)
+    rf = tile_block(tile_ms, (float(P) - 0.5 * E) * nn * R, 0.0, 2.0,
+                    "mm_tile_kernel<%d,3> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)" % ks,
+                    0.5 * E * nn * R)
+    # compulsory bytes per launch: iK once (shared by the batch) + per restart X-m, beta, hypers, s, outputs
+    alg_bytes = 8.0 * (E * nn + R * (n_c * D + E * n_c + 2 * E * D + D * D + D + E + E * E + D * E))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    traffic = None                       # dram bytes per launch of the same kernel/config from the committed ncu --set full capture
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_tile_traffic.json")))
-        if R == 32:
-            traffic = tj["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    roofline = {
-        "bound": "tensor", "kernel": "mm_tile_kernel<3,3> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)",
-        "achieved": achieved, "peak": peak_eff, "unit": "TFLOP/s", "frac": achieved / peak_eff, "traffic": traffic,
-        "traffic_source": "profiles/r01_s2_mm_tile_ncu_full.txt (ncu --set full, same kernel and config; ncu flushes the caches before the launch, in the pipeline the row operands written by the setup kernel are L2 hits)" if traffic else None,
-        "algorithmic_bytes": alg_bytes,
-        "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s), "
+    traffic = tsrc = None                # dram bytes per launch of the same kernel/config from the committed ncu --set full capture
+    if cfg is CONFIGS["metric"] and R == 32:
+        for fn in ("r02_tile_traffic.json", "r01_tile_traffic.json"):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", fn)))["dram_bytes_per_launch"]
+                tsrc = "profiles/" + fn + " (ncu --set full, same kernel and config; cold caches: in the pipeline the operands written by the setup kernel are L2 hits)"
+                break
+            except Exception:
+                pass
+    roofline = dict(rf)
+    roofline.update({
+        "bound": "tensor", "traffic": traffic, "traffic_source": tsrc,
+        "algorithmic_bytes": alg_bytes, "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+        "peak_source": "fp64 pipe measured live by pilco_microbench_fp64 (DFMA %.1f, DMMA %.1f TFLOP/s: 512 flop per warp-level DMMA.8x8x4), "
                        "time-weighted for this kernel's op mix; MEASURED_PEAKS.json holds no fp64 figure" % (dfma_tf, dmma_tf),
-        "pipe_busy_ncu": "fp64 pipe 26.6 % + DMMA (tensor) pipe 37.9 % of elapsed cycles, top stall math_pipe_throttle "
-                         "(profiles/r01_s2_mm_tile_ncu_full.txt, same kernel/config, R=32)",
-        "q_contraction_tflops": dot_flops / (tile_ms * 1e-3) / 1e12,
-        "tile_kernel_ms": tile_ms, "setup_kernel_ms": setup_ms,
+        "fp64_library_tflops": lib_tf,
+        "fp64_library_note": "cuBLAS DGEMM %d^3 through torch.matmul in this process: independent denominator only, not on the product path" % nmm,
+        "frac_of_library": (rf["achieved"] / lib_tf) if lib_tf else None,
+        "setup_kernel_ms": setup_ms,
         "hbm": {"achieved_gbs": alg_bytes / (tile_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": alg_bytes / (tile_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-    }
-    cpu_v, cores, sample = cpu_reference_steps_per_s(wl, reps=2, h_sample=4) if args.cpu_baseline else (None, 0, "skipped (--no-cpu-baseline)")
-    launches_per_step = nsplit * ((H * 8 + 1) + 1)                  # per sub-batch: ro_state + policy(setup1,setup2,tile,ro_policy) + dyn(setup1,setup2,tile); +memset
+    })
+    # whole step: SURVEY 8d flop + exp count of one rollout step x steps / measured time
+    F, Xe, Bs = step_counts(cfg)
+    step_flop_eq = F + EXP_FLOP_EQ * Xe
+    pipe_peak = min(dfma_tf, dmma_tf)
+    roofline["whole_step"] = {"flop_eq_per_rollout_step": step_flop_eq, "achieved": step_flop_eq * R * H / (ms_res * 1e-3) / 1e12,
+                              "peak": pipe_peak, "unit": "TFLOP/s", "frac": step_flop_eq * R * H / (ms_res * 1e-3) / 1e12 / pipe_peak,
+                              "compulsory_bytes_per_rollout_step": Bs}
+    fb = None
+    if ms_fb is not None:
+        fb = {"value": total_steps / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb,
+              "what": "taped forward cascade + tape-driven reverse sweep (policy gradient), device resident",
+              "e2e": {"value": total_steps / (ms_fb_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_fb_e2e,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_grad.numel()) * 8,
+                      "what": "pinned host policy parameters -> device, policy factorisation, taped forward, reverse sweep, [reward | gradient] -> host"}}
+        if ttile_ms:
+            # taped tile pass: every pair over its full square; per element the dot, the exp, the weight and column-sum
+            # updates (2 DFMA-class ops) and the second product H.[Z,1] (2 (D+1) flop)
+            fb["roofline"] = tile_block(ttile_ms, float(P) * nn * R, 2.0 * (D + 1), 4.0,
+                                        "mm_tape_tile_kernel<%d> (taped dynamics pass: Q-contraction + exp + H.[Z,1] product + column sums)" % ks, 0.0)
+            fb["roofline"]["bound"] = "tensor"
+    cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--no-cpu-baseline)"}
+    if args.cpu_baseline:
+        cr = CpuRollout(cfg, wl)
+        hs = 4 if n_c >= 200 else min(H, 10)
+        v, sample = cr.steps_per_s(reps=2, h=hs, budget_s=20.0)
+        cpu = {"value": v, "unit": UNIT, "cores": cr.threads, "kind": "port", "sample": sample, "host_cpus": os.cpu_count()}
+        if fb is not None:
+            vb, sb = cr.steps_per_s(reps=1, h=2 if n_c >= 200 else min(H, 6), grad=True, budget_s=20.0)
+            fb["cpu_baseline"] = {"value": vb, "unit": UNIT, "cores": cr.threads, "kind": "port", "sample": sb}
+    launches_per_rollout = (H * (8 if bf else 4) + 1) + 1      # per sub-batch: ro_state + [policy: setup1, setup2, tile, ro_policy] + dyn (setup1, setup2, tile); + memset
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "metric config: N=300 E=Ds=10 U=2 D=12 H=40, RBF policy bf=50, R=%d restarts/GPU, forward rollout" % R,
-                   "restarts_per_gpu": R, "graph": "one CUDA graph per rollout batch, %d sub-batches on parallel streams" % nsplit, "l2": "flushed between timed iterations (256 MiB write)", "finite": ok},
+        "config": {"workload": workload_string(cfg, R), "restarts_per_gpu": R,
+                   "graph": "one CUDA graph per rollout batch, %d sub-batches on parallel streams" % nsplit,
+                   "l2": "flushed between timed iterations (256 MiB write)", "finite": ok},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "what": "pinned host policy parameters -> device, policy factorisation, H-step rollout, rewards -> host"},
-        "fwd_bwd": ({"value": total_steps / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb,
-                     "what": "forward cascade + hand-derived reverse sweep (policy gradient), device resident"}
-                    if ms_fb is not None else None),
-        "gpu_launches": launches_per_step * args.steps,
+        "fwd_bwd": fb,
+        "api_predict": api,
+        "factorize_ms": fact_ms,
+        "gpu_launches": nsplit * launches_per_rollout * args.steps,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line))
@@ -461,15 +759,22 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--restarts", type=int, default=32, help="policy restarts per GPU")
-    ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward extra line")
-    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="tuning runs: skip the CPU leg")
+    ap.add_argument("--config", default="metric", choices=sorted(CONFIGS))
+    ap.add_argument("--restarts", type=int, default=0, help="policy restarts per GPU (default: the config's)")
+    ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward lines")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="tuning runs: skip the CPU legs")
+    ap.add_argument("--no-api-line", dest="api_line", action="store_false", help="skip the PILCO.predict class-API line")
     ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph")
+    ap.add_argument("--through-api", action="store_true", help="drive PILCO.optimize_policy itself (lock-step L-BFGS-B, sharded restarts)")
+    ap.add_argument("--maxiter", type=int, default=10, help="--through-api: L-BFGS-B iterations")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
+    elif args.through_api:
+        run_through_api(args, cfg)
     else:
-        run_ours(args)
+        run_ours(args, cfg)
 
 
 if __name__ == "__main__":

@@ -259,6 +259,10 @@ int    pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad*
 int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
                              double* M, double* S, double* V, int* info,
                              void* ws, size_t ws_bytes, float* ms_out, pilco_stream_t stream);
+int pilco_mm_forward_taped_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                                   double* M, double* S, double* V, int* info,
+                                   void* ws, size_t ws_bytes, void* tape, size_t tape_bytes,
+                                   float* ms_out, pilco_stream_t stream);
 int pilco_microbench_fp64(int which, int iters, int blocks, double* sink_dev, float* ms_out, pilco_stream_t stream);
 
 #ifdef __cplusplus

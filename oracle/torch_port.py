@@ -32,6 +32,26 @@ def calculate_factorizations(X, Y, ell, sf2, sn2):
     return iK, beta
 
 
+def fitc_factorizations(X, Z, Y, ell, sf2, sn2):
+    """smgpr.py:24-45 -> iK [E,M,M], beta [E,M] over the inducing points Z (batched over the outputs)."""
+    E, Mi = Y.shape[1], Z.shape[0]
+    eye = torch.eye(Mi, dtype=F64).expand(E, Mi, Mi)
+    Kmm = se_ard_K(Z, Z, ell, sf2) + 1e-6 * eye
+    Kmn = se_ard_K(Z, X, ell, sf2)
+    L = torch.linalg.cholesky(Kmm)
+    V = torch.linalg.solve_triangular(L, Kmn, upper=False)
+    G = torch.sqrt(1.0 + (sf2[:, None] - (V ** 2).sum(1)) / sn2[:, None])
+    V = V / G[:, None, :]
+    Am = torch.linalg.cholesky(V @ V.transpose(1, 2) + sn2[:, None, None] * eye)
+    At = L @ Am
+    iAt = torch.linalg.solve_triangular(At, eye, upper=False)
+    rhs = ((V / G[:, None, :]) @ Y.T[:, :, None])
+    tmp = torch.cholesky_solve(rhs, Am)
+    beta = torch.linalg.solve_triangular(L.transpose(1, 2), tmp, upper=True)[:, :, 0]
+    iK = torch.cholesky_solve(eye, L) - sn2[:, None, None] * (iAt.transpose(1, 2) @ iAt)
+    return iK, beta
+
+
 def predict_given_factorizations(C, ell, sf2, m, s, iK, beta):
     """mgpr.py:91-149; C = centres."""
     E, D = ell.shape

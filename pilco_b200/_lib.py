@@ -94,6 +94,8 @@ SIGNATURES = {
     "pilco_rollout_backward": (C.c_int, [C.POINTER(Rollout), C.POINTER(RolloutGrad), c_dp]),
     "pilco_mm_forward_profile": (C.c_int, [C.POINTER(GpModel), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                            c_dp, C.c_size_t, C.POINTER(C.c_float), c_dp]),
+    "pilco_mm_forward_taped_profile": (C.c_int, [C.POINTER(GpModel), C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                                                 c_dp, C.c_size_t, c_dp, C.c_size_t, C.POINTER(C.c_float), c_dp]),
     "pilco_microbench_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, c_dp, C.POINTER(C.c_float), c_dp]),
 }
 

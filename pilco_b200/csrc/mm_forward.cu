@@ -101,8 +101,39 @@ int pilco_mm_forward(const pilco_gp_model* gp, int R, const double* m, const dou
     return mm_forward_launch(p, (cudaStream_t)stream, true);
 }
 
-// Diagnostic: same work as pilco_mm_forward, with CUDA events around the three launches
-// (ms_out[0..2] = setup, tile, finish).  Synchronises; never call it in a captured region.
+// Diagnostic: same work as pilco_mm_forward (or, with a tape, pilco_mm_forward_taped), with CUDA events around the
+// three launches (ms_out[0..2] = setup, tile, finish).  Synchronises; never call it in a captured region.
+static int mm_forward_profile(MMParams& p, float* ms_out, cudaStream_t st) {
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
+    const int ks = ksteps_of(p.gp.D);
+    int rc;
+    cudaEventRecord(ev[0], st);
+    switch (ks) {
+        case 1: mm_setup_launch<4, false>(p, st); break;
+        case 2: mm_setup_launch<8, false>(p, st); break;
+        case 3: mm_setup_launch<12, false>(p, st); break;
+        default: mm_setup_launch<16, false>(p, st); break;
+    }
+    cudaEventRecord(ev[1], st);
+    if (p.tape != nullptr) rc = mm_tape_tile_launch(p, st);
+    else switch (ks) {
+        case 1: rc = launch_tile<1>(p, st); break;
+        case 2: rc = launch_tile<2>(p, st); break;
+        case 3: rc = launch_tile<3>(p, st); break;
+        default: rc = launch_tile<4>(p, st); break;
+    }
+    cudaEventRecord(ev[2], st);
+    mm_finish_kernel<<<p.R, 128, 0, st>>>(p);
+    cudaEventRecord(ev[3], st);
+    cudaEventSynchronize(ev[3]);
+    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    if (rc) return rc;
+    if (cudaGetLastError() != cudaSuccess) return PILCO_ERR_LAUNCH;
+    return PILCO_OK;
+}
+
 int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
                              double* M, double* S, double* V, int* info,
                              void* ws, size_t ws_bytes, float* ms_out, pilco_stream_t stream) {
@@ -114,33 +145,26 @@ int pilco_mm_forward_profile(const pilco_gp_model* gp, int R, const double* m, c
     p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D;
     p.M = M; p.S = S; p.V = V; p.info = info;
     p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; ++i) cudaEventCreate(&ev[i]);
-    const int E = gp->E, ks = ksteps_of(gp->D);
-    cudaEventRecord(ev[0], st);
-    switch (ks) {
-        case 1: mm_setup_launch<4, false>(p, st); break;
-        case 2: mm_setup_launch<8, false>(p, st); break;
-        case 3: mm_setup_launch<12, false>(p, st); break;
-        default: mm_setup_launch<16, false>(p, st); break;
-    }
-    cudaEventRecord(ev[1], st);
-    switch (ks) {
-        case 1: rc = launch_tile<1>(p, st); break;
-        case 2: rc = launch_tile<2>(p, st); break;
-        case 3: rc = launch_tile<3>(p, st); break;
-        default: rc = launch_tile<4>(p, st); break;
-    }
-    cudaEventRecord(ev[2], st);
-    mm_finish_kernel<<<R, 128, 0, st>>>(p);
-    cudaEventRecord(ev[3], st);
-    cudaEventSynchronize(ev[3]);
-    for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    return mm_forward_profile(p, ms_out, (cudaStream_t)stream);
+}
+
+int pilco_mm_forward_taped_profile(const pilco_gp_model* gp, int R, const double* m, const double* s,
+                                   double* M, double* S, double* V, int* info,
+                                   void* ws, size_t ws_bytes, void* tape, size_t tape_bytes,
+                                   float* ms_out, pilco_stream_t stream) {
+    int rc = mm_check_model(gp);
     if (rc) return rc;
-    if (cudaGetLastError() != cudaSuccess) return PILCO_ERR_LAUNCH;
-    return PILCO_OK;
+    if (!m || !s || !M || !S || !V || !ws || !tape || !ms_out) return PILCO_ERR_NULL;
+    if (pad64(gp->n) > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
+    if (ws_bytes < pilco_mm_workspace_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
+    const MMTapeL TL = mm_tape_layout(gp->n, gp->D, gp->E, R);
+    if (tape_bytes < TL.per_r * (size_t)R * sizeof(double)) return PILCO_ERR_WORKSPACE;
+    MMParams p;
+    p.gp = *gp; p.R = R; p.m = m; p.s = s; p.m_rs = gp->D; p.s_rs = (long long)gp->D * gp->D;
+    p.M = M; p.S = S; p.V = V; p.info = info;
+    p.ws = (double*)ws; p.L = mm_ws_layout(gp->n, gp->D, gp->E); p.bwd = 0; p.oQ = p.oC = p.oLd = 0;
+    p.tape = (double*)tape; p.TL = TL;
+    return mm_forward_profile(p, ms_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,33 +28,38 @@ int mm_tape_tile_launch(const MMParams& p, cudaStream_t st) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// reverse sweep from the tape: one CTA (256 threads) per task
+// reverse sweep from the tape: one CTA (4 warps) per task
 //   task <  E : mean / V block of output a   (per-centre weights recomputed: n exps, W-form of mgpr.py:103-118)
 //   task >= E : covariance block of the unordered pair q = task - E, from hr, hc, HZ on the tape
-// Both reduce to weighted moment sums over the centres,
-//   A1 = sum_n u_n z_n z_n',  A2 = sum_n v_n z_n z_n',  A3 = sum_n z_n HZ_n',  y1 = sum u_n z_n,  y2 = sum v_n z_n,
-// evaluated role-parallel (one matrix entry per thread) on 64-row chunks staged in shared memory.
+// Both reduce to weighted moment sums over the centres; with zx_n = [zeta_n, 1] (the 1 at index D) they are the three
+// products   zx' diag(u) zx,   zx' diag(v) zx,   zx' HZ   (K = n), evaluated with fp64 DMMA m8n8k4: the k-steps (4
+// centres each) are dealt round-robin to the warps, one value zx[row t][col g] per lane serves as A fragment
+// (A[m=col][k=row]) AND, scaled by u / v, as B fragment (B[k=row][n=col]).  A1 = block[:D,:D], y1 = block[:D, D],
+// sum u = block[D, D]; the symmetric blocks skip their lower tiles.
 // -------------------------------------------------------------------------------------------------
-#define TB_CHUNK 64
-#define TB_THREADS 256
+#define TB_THREADS 128
+#define TB_WARPS 4
 
 template <int DP>
-__global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBwd bp) {
+__global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd bp) {
     extern __shared__ __align__(16) double tb_dyn[];          // [2][np]: per-centre weights u, v
     const pilco_gp_model& gp = bp.gp;
     const MMTapeL& TL = bp.TL;
     const int n = gp.n, D = gp.D, E = gp.E, np = TL.np;
     const int r = blockIdx.y, task = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NSYM = DP * (DP + 1) / 2, NROLE = NSYM + DP * DP + 2 * DP + 2;
-    constexpr int ZS = DP + 1;                                  // odd row stride of the staged chunks
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int TX = (DP + 8) / 8;                            // 8-wide tiles covering [zeta, 1]: D + 1 <= 8 TX
+    constexpr int DX = 8 * TX;
+    constexpr int NSYMT = TX * (TX + 1) / 2;                    // upper tiles of a symmetric block
+    constexpr int NACC = 2 * (2 * NSYMT + TX * TX);             // accumulator doubles per lane
 
     __shared__ double sW[MAXD * SLD], sCm[MAXD * SLD], sT[MAXD * SLD], sX[MAXD * SLD];
     __shared__ double sinvd[MAXD], spa[MAXD], spb[MAXD], sgv[MAXD], swgv[MAXD], sm[MAXD];
-    __shared__ double sA1[DP * DP], sA2[DP * DP], sA3[DP * DP], sy1[DP], sy2[DP], ssum[2], sscal[4];
-    __shared__ double sZc[TB_CHUNK * ZS], sHc[TB_CHUNK * ZS];
+    __shared__ double sA1[DX * DX], sA2[DX * DX], sA3[DX * DX], sscal[4];
     double* su = tb_dyn;
     double* sv = tb_dyn + np;
+    double* sRed = tb_dyn + 2 * (size_t)np;                    // [(TB_WARPS - 1)][NACC][32] cross-warp reduction
 
     const double* X = gp.X + (size_t)r * gp.X_bs;
     const double* ell = gp.ell + (size_t)r * gp.ell_bs;
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBw
     double* part = bp.part + ((size_t)r * (E + TL.P) + task) * (MAXD + (size_t)D * D);
     double* Tm = part;
     double* Ts = part + MAXD;
-    if (tid < DP) sm[tid] = tid < D ? mr[tid] : 0.0;
+    if (tid < MAXD) sm[tid] = tid < D ? mr[tid] : 0.0;
 
     const bool is_out = task < E;
     int a = task, b = task, q = 0;
@@ -157,66 +162,90 @@ __global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBw
         }
         HZg = tpr + TL.HZ + (size_t)q * np * TL.ldh;
     }
+    __syncthreads();
 
-    // ---- weighted moment sums, role-parallel ----
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-    for (int c0 = 0; c0 < n; c0 += TB_CHUNK) {
-        __syncthreads();                                            // su/sv written; previous chunk consumed
-        for (int e = tid; e < TB_CHUNK * DP; e += blockDim.x) {
-            const int k = e / DP, d = e % DP, nn = c0 + k;
-            const bool in = nn < n && d < D;
-            sZc[k * ZS + d] = in ? X[(size_t)nn * D + d] - sm[d] : 0.0;
-            sHc[k * ZS + d] = (in && HZg) ? HZg[(size_t)nn * TL.ldh + d] : 0.0;
-        }
-        __syncthreads();
-        const int rows = (n - c0) < TB_CHUNK ? (n - c0) : TB_CHUNK;
+    // ---- weighted moment sums by DMMA ----
+    double cu[NSYMT][2], cv[NSYMT][2], ch[TX * TX][2];
 #pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
-            const int role = tid + TB_THREADS * slot;
-            if (role >= NROLE) break;
-            double a1 = acc[slot][0], a2 = acc[slot][1];
-            if (role < NSYM) {                                      // (i <= j) of A1 and A2
-                int j = 0;
-                while ((j + 1) * (j + 2) / 2 <= role) ++j;
-                const int i = role - j * (j + 1) / 2;
-                for (int k = 0; k < rows; ++k) {
-                    const double pz = sZc[k * ZS + i] * sZc[k * ZS + j];
-                    a1 = fma(su[c0 + k], pz, a1); a2 = fma(sv[c0 + k], pz, a2);
-                }
-            } else if (role < NSYM + DP * DP) {                     // A3[i][j] = sum_n z_n[i] HZ_n[j]
-                const int e = role - NSYM, i = e / DP, j = e % DP;
-                if (HZg) for (int k = 0; k < rows; ++k) a1 = fma(sZc[k * ZS + i], sHc[k * ZS + j], a1);
-            } else if (role < NSYM + DP * DP + DP) {                // y1[i], y2[i]
-                const int i = role - NSYM - DP * DP;
-                for (int k = 0; k < rows; ++k) { a1 = fma(su[c0 + k], sZc[k * ZS + i], a1); a2 = fma(sv[c0 + k], sZc[k * ZS + i], a2); }
-            } else if (role == NSYM + DP * DP + DP) {               // sum u, sum v
-                for (int k = 0; k < rows; ++k) { a1 += su[c0 + k]; a2 += sv[c0 + k]; }
+    for (int i = 0; i < NSYMT; ++i) { cu[i][0] = cu[i][1] = cv[i][0] = cv[i][1] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < TX * TX; ++i) { ch[i][0] = ch[i][1] = 0.0; }
+    const int nks = (n + 3) >> 2;
+    for (int ks = warp; ks < nks; ks += TB_WARPS) {
+        const int row = 4 * ks + t;
+        const bool live = row < n;
+        const double u = su[row], v = sv[row];                  // (0 beyond n: su/sv are np long, np >= 4 nks)
+        double zx[TX], bu[TX], bv[TX], bh[TX];
+#pragma unroll
+        for (int tl = 0; tl < TX; ++tl) {
+            const int c = g + 8 * tl;
+            double z = 0.0, h = 0.0;
+            if (live) {
+                if (c < D) { z = X[(size_t)row * D + c] - sm[c]; if (HZg) h = HZg[(size_t)row * TL.ldh + c]; }
+                else if (c == D) z = 1.0;
             }
-            acc[slot][0] = a1; acc[slot][1] = a2;
+            zx[tl] = z; bu[tl] = u * z; bv[tl] = v * z; bh[tl] = h;
         }
-    }
+        int si = 0;
 #pragma unroll
-    for (int slot = 0; slot < 2; ++slot) {
-        const int role = tid + TB_THREADS * slot;
-        if (role >= NROLE) break;
-        const double a1 = acc[slot][0], a2 = acc[slot][1];
-        if (role < NSYM) {
-            int j = 0;
-            while ((j + 1) * (j + 2) / 2 <= role) ++j;
-            const int i = role - j * (j + 1) / 2;
-            sA1[i * DP + j] = a1; sA1[j * DP + i] = a1; sA2[i * DP + j] = a2; sA2[j * DP + i] = a2;
-        } else if (role < NSYM + DP * DP) sA3[role - NSYM] = a1;
-        else if (role < NSYM + DP * DP + DP) { sy1[role - NSYM - DP * DP] = a1; sy2[role - NSYM - DP * DP] = a2; }
-        else if (role == NSYM + DP * DP + DP) { ssum[0] = a1; ssum[1] = a2; }
+        for (int mt = 0; mt < TX; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < TX; ++nt) {
+                if (nt >= mt) {
+                    dmma884(cu[si][0], cu[si][1], zx[mt], bu[nt]);
+                    dmma884(cv[si][0], cv[si][1], zx[mt], bv[nt]);
+                    ++si;
+                }
+                if (!is_out) dmma884(ch[mt * TX + nt][0], ch[mt * TX + nt][1], zx[mt], bh[nt]);
+            }
+    }
+    // cross-warp reduction (fixed order), then warp 0 scatters the C fragments into square matrices
+    if (warp > 0) {
+        double* dst = sRed + ((size_t)(warp - 1) * NACC) * 32 + lane;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < NSYMT; ++i) { dst[32 * k++] = cu[i][0]; dst[32 * k++] = cu[i][1]; dst[32 * k++] = cv[i][0]; dst[32 * k++] = cv[i][1]; }
+#pragma unroll
+        for (int i = 0; i < TX * TX; ++i) { dst[32 * k++] = ch[i][0]; dst[32 * k++] = ch[i][1]; }
     }
     __syncthreads();
+    if (warp == 0) {
+        for (int w = 0; w < TB_WARPS - 1; ++w) {
+            const double* src = sRed + ((size_t)w * NACC) * 32 + lane;
+            int k = 0;
+#pragma unroll
+            for (int i = 0; i < NSYMT; ++i) { cu[i][0] += src[32 * k++]; cu[i][1] += src[32 * k++]; cv[i][0] += src[32 * k++]; cv[i][1] += src[32 * k++]; }
+#pragma unroll
+            for (int i = 0; i < TX * TX; ++i) { ch[i][0] += src[32 * k++]; ch[i][1] += src[32 * k++]; }
+        }
+        int si = 0;
+#pragma unroll
+        for (int mt = 0; mt < TX; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < TX; ++nt) {
+                const int i = 8 * mt + g, j = 8 * nt + 2 * t;
+                if (nt >= mt) {
+                    sA1[i * DX + j] = cu[si][0]; sA1[i * DX + j + 1] = cu[si][1];
+                    sA2[i * DX + j] = cv[si][0]; sA2[i * DX + j + 1] = cv[si][1];
+                    if (nt > mt) {
+                        sA1[j * DX + i] = cu[si][0]; sA1[(j + 1) * DX + i] = cu[si][1];
+                        sA2[j * DX + i] = cv[si][0]; sA2[(j + 1) * DX + i] = cv[si][1];
+                    }
+                    ++si;
+                }
+                sA3[i * DX + j] = ch[mt * TX + nt][0]; sA3[i * DX + j + 1] = ch[mt * TX + nt][1];
+            }
+    }
+    __syncthreads();
+    // A1 = sA1[:D,:D] etc.; y1[i] = sA1[i][D], y2[i] = sA2[i][D]; sum u = sA1[D][D], sum v = sA2[D][D]
+    const double sum_u = sA1[D * DX + D], sum_v = sA2[D * DX + D];
 
     if (is_out) {
         // gW = -0.5 A1 + sym(gV y2');  gA = -W gW W - 0.5 glogc W;  sum gzeta = -W y1 + (sum w) W gV
-        const double glogc = ssum[0];
+        const double glogc = sum_u;
         for (int e = tid; e < DP * DP; e += blockDim.x) {
             const int i = e / DP, j = e % DP;
-            sT[i * SLD + j] = -0.5 * sA1[e] + 0.5 * (sgv[i] * sy2[j] + sgv[j] * sy2[i]);
+            sT[i * SLD + j] = (i < D && j < D) ? -0.5 * sA1[i * DX + j] + 0.5 * (sgv[i] * sA2[j * DX + D] + sgv[j] * sA2[i * DX + D]) : 0.0;
         }
         __syncthreads();
         for (int e = tid; e < DP * DP; e += blockDim.x) {           // sCm = W gW
@@ -232,23 +261,23 @@ __global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBw
             for (int k = 0; k < DP; ++k) v = fma(sCm[i * SLD + k], sW[k * SLD + j], v);
             Ts[e] = -v - 0.5 * glogc * sW[i * SLD + j];
         }
-        if (tid < DP) {
+        if (tid < D) {
             double v = 0.0;
-            for (int j = 0; j < DP; ++j) v = fma(sW[tid * SLD + j], sy1[j], v);
-            Tm[tid] = v - ssum[1] * swgv[tid];                      // -(sum_n gzeta_n)
+            for (int j = 0; j < D; ++j) v = fma(sW[tid * SLD + j], sA1[j * DX + D], v);
+            Tm[tid] = v - sum_v * swgv[tid];                        // -(sum_n gzeta_n)
         }
         return;
     }
 
     // pair task
-    const double g = (a == b) ? gS[a * E + a] : gS[a * E + b] + gS[b * E + a];
-    const double glogR = -0.5 * g * ssum[0];
+    const double gw = (a == b) ? gS[a * E + a] : gS[a * E + b] + gS[b * E + a];
+    const double glogR = -0.5 * gw * sum_u;
     for (int e = tid; e < DP * DP; e += blockDim.x) {               // sT = gQ / (delta_i delta_j)
         const int i = e / DP, j = e % DP;
         double v = 0.0;
         if (i < D && j < D) {
-            const double gq = g * (spa[i] * spa[j] * sA1[e] + spb[i] * spb[j] * sA2[e]
-                                   + spa[i] * spb[j] * sA3[i * DP + j] + spa[j] * spb[i] * sA3[j * DP + i]);
+            const double gq = gw * (spa[i] * spa[j] * sA1[i * DX + j] + spb[i] * spb[j] * sA2[i * DX + j]
+                                    + spa[i] * spb[j] * sA3[i * DX + j] + spa[j] * spb[i] * sA3[j * DX + i]);
             v = gq / ((spa[i] + spb[i]) * (spa[j] + spb[j]));
         }
         sT[i * SLD + j] = v;
@@ -267,45 +296,32 @@ __global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBw
         for (int k = 0; k < D; ++k) v = fma(sX[i * SLD + k], sCm[k * SLD + j], v);
         Ts[e] = 0.5 * v + glogR * sCm[i * SLD + j];
     }
-    if (tid < DP) {                                                 // -(sum gzeta) = g (u - 2 delta o Q u),  u = p_a y1 + p_b y2
+    if (tid < D) {                                                  // -(sum gzeta) = g (u - 2 delta o Q u),  u = p_a y1 + p_b y2
         double qu = 0.0;
-        for (int j = 0; j < DP; ++j) qu = fma(sW[tid * SLD + j], spa[j] * sy1[j] + spb[j] * sy2[j], qu);
-        const double u = spa[tid] * sy1[tid] + spb[tid] * sy2[tid];
-        Tm[tid] = g * (u - 2.0 * (spa[tid] + spb[tid]) * qu);
+        for (int j = 0; j < D; ++j) qu = fma(sW[tid * SLD + j], spa[j] * sA1[j * DX + D] + spb[j] * sA2[j * DX + D], qu);
+        const double u = spa[tid] * sA1[tid * DX + D] + spb[tid] * sA2[tid * DX + D];
+        Tm[tid] = gw * (u - 2.0 * (spa[tid] + spb[tid]) * qu);
     }
 }
 
 // sum the task partials -> gm, gs
 __global__ void __launch_bounds__(128) mm_tape_breduce_kernel(MMTapeBwd bp) {
-    const int D = bp.gp.D, E = bp.gp.E;
-    const int ntask = E + bp.TL.P;
-    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const size_t stride = MAXD + (size_t)D * D;
-    const double* part = bp.part + (size_t)r * ntask * stride;
-    double* gm = bp.gm + (size_t)r * bp.gm_rs;
-    double* gs = bp.gs + (size_t)r * bp.gs_rs;
-    for (int d = tid; d < D; d += nt) {
-        double v = 0.0;
-        for (int tk = 0; tk < ntask; ++tk) v += part[(size_t)tk * stride + d];
-        gm[d] = bp.accumulate ? gm[d] + v : v;
-    }
-    for (int e = tid; e < D * D; e += nt) {
-        const int i = e / D, j = e % D;
-        double v = 0.0;
-        for (int tk = 0; tk < ntask; ++tk)
-            v += 0.5 * (part[(size_t)tk * stride + MAXD + i * D + j] + part[(size_t)tk * stride + MAXD + j * D + i]);
-        gs[e] = bp.accumulate ? gs[e] + v : v;
-    }
+    const int r = blockIdx.x;
+    mm_tape_reduce_device(bp.part + (size_t)r * mm_tape_bwd_part_doubles(bp.gp.D, bp.gp.E), bp.gp.E + bp.TL.P, bp.gp.D,
+                          bp.gm + (size_t)r * bp.gm_rs, bp.gs + (size_t)r * bp.gs_rs, bp.accumulate);
 }
 
-int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st) {
+int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_reduce) {
     const int E = bp.gp.E, R = bp.R;
     dim3 gf(E + bp.TL.P, R);
-    const size_t smem = (size_t)2 * bp.TL.np * sizeof(double);
+    // dynamic shared memory: per-centre weights [2][np] + the cross-warp reduction buffer [3][NACC][32]
+    const int dp = 4 * ksteps_of(bp.gp.D), tx = (dp + 8) / 8;
+    const int nacc = 2 * (tx * (tx + 1) + tx * tx);
+    const size_t smem = ((size_t)2 * bp.TL.np + (size_t)(TB_WARPS - 1) * nacc * 32) * sizeof(double);
     static bool configured_dev[PILCO_MAX_DEVICES] = {false};
     bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {                                          // large n: static + dynamic shared memory > 48 KB
-        const int big = 2 * TAPE_MAX_NP * (int)sizeof(double);
+        const int big = (2 * TAPE_MAX_NP + (TB_WARPS - 1) * 42 * 32) * (int)sizeof(double);
         if (cudaFuncSetAttribute(mm_tape_bfinish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_bfinish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_bfinish_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
@@ -320,8 +336,10 @@ int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st) {
         default: mm_tape_bfinish_kernel<16><<<gf, TB_THREADS, smem, st>>>(bp); break;
     }
     CUDA_LAUNCH_CHECK();
-    mm_tape_breduce_kernel<<<R, 128, 0, st>>>(bp);
-    CUDA_LAUNCH_CHECK();
+    if (with_reduce) {
+        mm_tape_breduce_kernel<<<R, 128, 0, st>>>(bp);
+        CUDA_LAUNCH_CHECK();
+    }
     return PILCO_OK;
 }
 
@@ -373,7 +391,7 @@ int pilco_mm_backward_taped(const pilco_gp_model* gp, int R, const double* m, co
     bp.tape = (const double*)tape; bp.TL = mm_tape_layout(gp->n, gp->D, gp->E, R);
     bp.part = (double*)ws; bp.gm = gm; bp.gs = gs; bp.gm_rs = gp->D; bp.gs_rs = (long long)gp->D * gp->D;
     bp.accumulate = 0;
-    return mm_tape_backward_launch(bp, (cudaStream_t)stream);
+    return mm_tape_backward_launch(bp, (cudaStream_t)stream, true);
 }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
                                            double* __restrict__ sCsw, int lane) {
     constexpr int ldz = KS == 1 ? 4 : (KS <= 3 ? 12 : 20);
     constexpr int NT = (4 * KS + 7) / 8;
+    constexpr bool ONES = (KS & 1) != 0;                       // DP = 4 KS = 4 (mod 8)
     const int g = lane >> 2, t = lane & 3;
     const int pg = (g >> 1) | ((g & 1) << 2);                  // pi(g)
     for (int cg = cbeg; cg < cend; cg += 8) {
@@ -85,6 +86,9 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
         for (int k2 = 0; k2 < 2; ++k2)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) zb[k2][nt] = sZ[(size_t)(cg + 4 * k2 + t) * ldz + 8 * nt + g];
+        // DP = 4 (mod 8): column DP of the last n-tile is free -- a column of ones there makes the second product
+        // deliver the row sums as HZ[:, DP] (lanes t == 2, element 0) and saves the explicit adds
+        if (ONES && g == 4) { zb[0][NT - 1] = 1.0; zb[1][NT - 1] = 1.0; }
         double cs0 = 0.0, cs1 = 0.0;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
@@ -100,7 +104,7 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
             } else {
                 w0 = bb0 * l0; w1 = bb1 * l1;
             }
-            hl[j] += w0 + w1;
+            if (!ONES) hl[j] += w0 + w1;
             cs0 = fma(rf[j], w0, cs0); cs1 = fma(rf[j], w1, cs1);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
@@ -208,11 +212,17 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
             double v = 0.0;
             if (oct[j] < NO) {
                 const int row = 8 * oct[j] + g;
-                double h = hl[j];
-                h += __shfl_xor_sync(0xffffffffu, h, 1);
-                h += __shfl_xor_sync(0xffffffffu, h, 2);
+                constexpr bool ONES = (KS & 1) != 0;
+                constexpr int tsum = ONES ? 2 : 0;              // lane of the quad that holds the row sum
+                double h;
+                if (ONES) h = hz[j][NT - 1][0];                 // HZ[:, DP] (ones column of the second product)
+                else {
+                    h = hl[j];
+                    h += __shfl_xor_sync(0xffffffffu, h, 1);
+                    h += __shfl_xor_sync(0xffffffffu, h, 2);
+                }
                 const double hrv = rf[j] * h;
-                if (t == 0) { tpr[TL.hr + (size_t)q * np + row] = hrv; v = hrv; }
+                if (t == tsum) { tpr[TL.hr + (size_t)q * np + row] = hrv; v = hrv; }
                 double* hzrow = tpr + TL.HZ + ((size_t)q * np + row) * TL.ldh;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
@@ -260,4 +270,40 @@ struct MMTapeBwd {
 static inline __host__ __device__ size_t mm_tape_bwd_part_doubles(int D, int E) {
     return (size_t)(E + npairs_of(E)) * (MAXD + (size_t)D * D);
 }
-int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st);
+// with_reduce = false: the caller's next kernel sums the task partials itself (mm_tape_reduce_device)
+int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_reduce);
+
+#ifdef __CUDACC__
+// sum of the task partials of one restart -> gm [D], gs [D,D] (symmetrised); all threads of the CTA take part.
+// Fixed order over the tasks (deterministic); 4 independent partial sums per element hide the load latency.
+__device__ __forceinline__ void mm_tape_reduce_device(const double* __restrict__ part, int ntask, int D,
+                                                      double* __restrict__ gm, double* __restrict__ gs, int accumulate) {
+    const size_t stride = MAXD + (size_t)D * D;
+    for (int e = threadIdx.x; e < D + D * D; e += blockDim.x) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        if (e < D) {
+            const double* p0 = part + e;
+            int tk = 0;
+            for (; tk + 3 < ntask; tk += 4) {
+                v0 += p0[(size_t)tk * stride]; v1 += p0[(size_t)(tk + 1) * stride];
+                v2 += p0[(size_t)(tk + 2) * stride]; v3 += p0[(size_t)(tk + 3) * stride];
+            }
+            for (; tk < ntask; ++tk) v0 += p0[(size_t)tk * stride];
+            const double v = (v0 + v1) + (v2 + v3);
+            gm[e] = accumulate ? gm[e] + v : v;
+        } else {
+            const int k = e - D, i = k / D, j = k % D;
+            const double* p0 = part + MAXD + i * D + j;
+            const double* p1 = part + MAXD + j * D + i;
+            int tk = 0;
+            for (; tk + 1 < ntask; tk += 2) {
+                v0 += p0[(size_t)tk * stride]; v1 += p1[(size_t)tk * stride];
+                v2 += p0[(size_t)(tk + 1) * stride]; v3 += p1[(size_t)(tk + 1) * stride];
+            }
+            for (; tk < ntask; ++tk) { v0 += p0[(size_t)tk * stride]; v1 += p1[(size_t)tk * stride]; }
+            const double v = 0.5 * ((v0 + v1) + (v2 + v3));
+            gs[k] = accumulate ? gs[k] + v : v;
+        }
+    }
+}
+#endif

@@ -58,6 +58,8 @@ struct RbDev {
     // cotangent buffers [R, len]
     double *gm, *gS, *gMd, *gSd, *gVd, *gmj, *gsj, *gsjx, *gMp, *gSp, *gVp;
     double *gW, *gb;      // linear policy gradient accumulators [R,U,Ds], [R,U]
+    // taped dynamics VJP: task partials [R][ntask][MAXD + D*D] that rb_post sums into gmj / gsj itself (else NULL)
+    const double* tpart; int tp_ntask;
 };
 
 __global__ void __launch_bounds__(128) rb_pre_kernel(RbDev p) {
@@ -92,6 +94,11 @@ __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
     const int tid = threadIdx.x, nt = blockDim.x;
     double* gm = p.gm + (size_t)r * Ds;
     double* gS = p.gS + (size_t)r * Ds * Ds;
+    if (p.tpart) {                                            // fold mm_tape_breduce into this kernel
+        mm_tape_reduce_device(p.tpart + (size_t)r * p.tp_ntask * (MAXD + (size_t)D * D), p.tp_ntask, D,
+                              p.gmj + (size_t)r * D, p.gsj + (size_t)r * D * D, 0);
+        __syncthreads();
+    }
     const double* gmj = p.gmj + (size_t)r * D;
     const double* gsj = p.gsj + (size_t)r * D * D;
     const double* gsjx = p.gsjx + (size_t)r * D * D;
@@ -162,9 +169,10 @@ __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
     }
 }
 
-// VJP through beta_a = (K_a + sn2 I)^-1 y_a for the RBF policy (sf2 = 1): given gy_a = (K_a+sn2 I)^-1 gbeta_a,
+// VJP through beta_a = (K_a + sn2 I)^-1 y_a for the RBF policy (sf2 frozen, controllers.py:91-93): given gy_a = (K_a+sn2 I)^-1 gbeta_a,
 //   gY[:,a] = gy_a ;  gK = -gy beta^T ;  gX += ..., gell += ...   (oracle/staged.py: rbf_factor_backward)
 __global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int U, const double* X, const double* ell,
+                                                             const double* sf2, long long sf2_bs,
                                                              const double* beta, const double* gy,
                                                              double* gX, double* gY, double* gell) {
     // one CTA per restart, thread n owns centre n: K[n][m] is evaluated once per (n, m, a)
@@ -177,6 +185,7 @@ __global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int
     for (int e = tid; e < bf * U; e += nt) { const int n = e / U, a = e % U; gY[(size_t)r * bf * U + e] = gr[a * bf + n]; }
     for (int a = 0; a < U; ++a) {
         double il2[MAXD], accl[MAXD];
+        const double sfa = sf2[(size_t)r * sf2_bs + a];
 #pragma unroll
         for (int d = 0; d < MAXD; ++d) { il2[d] = d < Ds ? 1.0 / (lr[a * Ds + d] * lr[a * Ds + d]) : 0.0; accl[d] = 0.0; }
         for (int n = tid; n < bf; n += nt) {
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int
                     diff[d] = d < Ds ? xn[d] - Xr[m * Ds + d] : 0.0;
                     d2 = fma(diff[d] * diff[d], il2[d], d2);
                 }
-                const double K = exp(-0.5 * d2);
+                const double K = sfa * exp(-0.5 * d2);
                 const double gK = -gyn * br[a * bf + m] * K;                // dL/dK[n][m] * K
                 const double Psym = gK - gr[a * bf + m] * bn * K;          // (gK + gK^T)[n][m] * K
 #pragma unroll
@@ -259,6 +268,8 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
     d.gmj = buf(BL.gmj); d.gsj = buf(BL.gsj); d.gsjx = buf(BL.gsjx);
     d.gMp = buf(BL.gMp); d.gSp = buf(BL.gSp); d.gVp = buf(BL.gVp);
     d.gW = g->gW; d.gb = g->gb;
+    d.tpart = ro->tape ? bws + BL.dynb : nullptr;
+    d.tp_ntask = ro->dyn.E + npairs_of(ro->dyn.E);
 
     for (int t = H - 1; t >= 0; --t) {
         d.t = t;
@@ -277,7 +288,7 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
             tb.tape = (const double*)ro->tape + (size_t)t * RR * tb.TL.per_r;
             tb.part = bws + BL.dynb;
             tb.gm = d.gmj; tb.gm_rs = D; tb.gs = d.gsj; tb.gs_rs = (long long)D * D; tb.accumulate = 0;
-            rc = mm_tape_backward_launch(tb, st);
+            rc = mm_tape_backward_launch(tb, st, false);        // rb_post sums the task partials
         } else {
             MMBwdParams bp = mm_bwd_params(&ro->dyn, R, slot(FL.mj, D, t), D, slot(FL.sj, (size_t)D * D, t), (long long)D * D,
                                            slot(FL.Md, Ds, t), d.gMd, d.gSd, d.gVd,
@@ -302,7 +313,8 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
         const int ldw = pad64(bf);
         chol_solve_vec_launch(st, R * U, bf, g->pol_L, ldw, (long long)ldw * ldw, U,
                               buf(BL.gbeta), (long long)U * bf, bf, 1, buf(BL.gy), bf);
-        rbf_factor_bwd_kernel<<<R, 128, 0, st>>>(bf, Ds, U, ro->pol.rbf.X, ro->pol.rbf.ell, ro->pol.rbf.beta,
+        rbf_factor_bwd_kernel<<<R, 128, 0, st>>>(bf, Ds, U, ro->pol.rbf.X, ro->pol.rbf.ell, ro->pol.rbf.sf2, ro->pol.rbf.sf2_bs,
+                                                  ro->pol.rbf.beta,
                                                   buf(BL.gy), g->gXc, g->gYc, g->gell);
         CUDA_LAUNCH_CHECK();
     }

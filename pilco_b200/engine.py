@@ -413,6 +413,54 @@ class RolloutPlan:
         return self.gbuf
 
 
+class PredictPlan:
+    """``PILCO.predict(m, S, n)`` as ONE graph launch: host moments -> device, n-step cascade (R = 1), final
+    moments + reward + status -> pinned host memory.  Built once per (model, policy, reward, n) state by
+    ``PILCO`` and replayed for every call with new initial moments (pilco/models/pilco.py:118-136)."""
+
+    def __init__(self, dyn, policy_spec, reward_terms, Ds, n, mult_mu=0.0):
+        d = device()
+        self.Ds, self.n = int(Ds), int(n)
+        Ds = self.Ds
+        self.h_in = torch.zeros(Ds + Ds * Ds, dtype=F64).pin_memory()
+        self.h_out = torch.zeros(Ds + Ds * Ds + 2, dtype=F64).pin_memory()       # [m | S | reward | info]
+        self.d_in = torch.zeros(Ds + Ds * Ds, dtype=F64, device=d)
+        self.d_out = torch.zeros(Ds + Ds * Ds + 2, dtype=F64, device=d)
+        self.plan = RolloutPlan(dyn, policy_spec, reward_terms, np.zeros(Ds), np.eye(Ds), self.n, R=1, mult_mu=mult_mu)
+        self._enqueue()                                    # eager warm-up (one-time kernel attributes)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+
+    def _enqueue(self):
+        Ds, p = self.Ds, self.plan
+        self.d_in.copy_(self.h_in, non_blocking=True)
+        p.m0.copy_(self.d_in[:Ds])
+        p.S0.copy_(self.d_in[Ds:].reshape(Ds, Ds))
+        p.forward()
+        out = self.d_out
+        out[:Ds] = p.traj_m[0, -1]
+        out[Ds:Ds + Ds * Ds] = p.traj_S[0, -1].reshape(-1)
+        out[Ds + Ds * Ds] = p.reward[0]
+        out[Ds + Ds * Ds + 1] = p.info[0].to(F64)
+        self.h_out.copy_(out, non_blocking=True)
+
+    def __call__(self, m, S):
+        """m [Ds] / [1,Ds], S [Ds,Ds] (host) -> (m_n [1,Ds], S_n [Ds,Ds], reward [1,1]) host ndarrays"""
+        Ds = self.Ds
+        hin = self.h_in.numpy()
+        hin[:Ds] = np.asarray(m, dtype=np.float64).reshape(Ds)
+        hin[Ds:] = np.asarray(S, dtype=np.float64).reshape(Ds * Ds)
+        self.graph.replay()
+        torch.cuda.current_stream().synchronize()
+        res = self.h_out.numpy()
+        if res[-1] != 0.0:
+            raise RuntimeError("moment-matching rollout failed: covariance not positive definite")
+        return (res[:Ds].reshape(1, Ds).copy(), res[Ds:Ds + Ds * Ds].reshape(Ds, Ds).copy(),
+                res[Ds + Ds * Ds].reshape(1, 1).copy())
+
+
 class SplitRollout:
     """R independent rollouts as ``nsplit`` sub-batches on parallel streams inside ONE captured CUDA graph.
 

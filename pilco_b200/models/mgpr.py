@@ -197,12 +197,33 @@ class MGPR:
         """(iK [E,n,n], beta [E,n]) as CUDA tensors  (mgpr.py:81-89)."""
         gp = self.device_gp()
         iK = gp.iK[:, :gp.n, :gp.n] if gp.iK is not None else None
+        self._last_fact = (iK, gp.beta, self._cache_key)
         return iK, gp.beta
 
+    def _gp_from_factors(self, iK, beta):
+        """Temporary device model around caller-supplied factors (any array-like [E,n,n] / [E,n]): the reference's
+        predict_given_factorizations computes with whatever it is handed (mgpr.py:91-149; RbfController passes
+        ``0.0 * iK``, controllers.py:116), so custom / modified factors must drive the result here too."""
+        base = self.device_gp()
+        n, E = base.n, base.E
+        beta_d = engine.dev(beta.detach() if isinstance(beta, torch.Tensor) else beta).reshape(E, n)
+        iK_d = engine.dev(iK.detach() if isinstance(iK, torch.Tensor) else iK).reshape(E, n, n)
+        ldk = engine.pad_n(n)
+        pad = torch.zeros((E, ldk, ldk), dtype=torch.float64, device=iK_d.device)
+        pad[:, :n, :n] = iK_d
+        return engine.DeviceGP(base.X, base.ell, base.sf2, beta_d, pad, ldk, mode=0)
+
     def predict_given_factorizations(self, m, s, iK=None, beta=None):
-        """mgpr.py:91-149 on the device; the cached factorisation is used (iK/beta arguments are accepted
-        for signature compatibility and must come from ``calculate_factorizations``)."""
+        """mgpr.py:91-149 on the device.  With no factors, or with exactly the objects ``calculate_factorizations``
+        returned for the current state, the cached device model is used; any other ``iK`` / ``beta`` is honoured
+        (a temporary device model is built from them) -- never silently ignored."""
         gp = self.device_gp()
+        last = getattr(self, "_last_fact", None)
+        own = last is not None and last[2] == self._cache_key and iK is last[0] and beta is last[1]
+        if (iK is None) != (beta is None):
+            raise ValueError("predict_given_factorizations: pass both iK and beta (or neither)")
+        if iK is not None and not own:
+            gp = self._gp_from_factors(iK, beta)
         m = np.asarray(m, dtype=np.float64).reshape(1, -1)
         s = np.asarray(s, dtype=np.float64).reshape(1, gp.D, gp.D)
         M, S, V, info = engine.mm_forward(gp, m, s)

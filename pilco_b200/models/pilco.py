@@ -55,9 +55,13 @@ class PILCO:
                 gp = c.device_gp()
             else:
                 X, Y, th = c.split_flat(flats)
-                ell = 1e-3 + np.logaddexp(0.0, th)
+                ell = c.models[0].kernel.lengthscales.transform.forward(th)      # lower + softplus (controllers.py:100)
                 R = X.shape[0]
-                gp = engine.gp_factorize(X, Y, ell, np.ones((R, U)), 1e-4 * np.ones((R, U)), need_iK=False, mode=1)
+                # kernel variance and noise are the controller's own Parameters (sf2 = 1 and sn2 = 1e-4 unless the
+                # user changed them, controllers.py:77-78,91-93) -- the same values compute_reward()/predict() see
+                sf2 = np.tile(np.asarray(c.variance, dtype=np.float64).reshape(1, U), (R, 1))
+                sn2 = np.tile(np.asarray(c.noise, dtype=np.float64).reshape(1, U), (R, 1))
+                gp = engine.gp_factorize(X, Y, ell, sf2, sn2, need_iK=False, mode=1)
             return dict(kind=_lib.POLICY_RBF, Ds=Ds, U=U, squash=True,
                         max_action=controllers._max_action_vec(c.max_action, U), gp=gp)
         raise TypeError("unsupported controller type %r" % type(c))
@@ -73,13 +77,37 @@ class PILCO:
                                   np.asarray(m_x, dtype=np.float64).reshape(-1),
                                   np.asarray(s_x, dtype=np.float64), int(n), R=R, mult_mu=mult_mu)
 
+    def _reward_key(self):
+        terms, mult_mu = self.reward_spec()
+        parts = [repr(float(mult_mu))]
+        for t in terms:
+            parts.append(repr((int(t["kind"]), float(t.get("coef", 1.0)), int(t.get("channel", 0)))))
+            parts.append(np.ascontiguousarray(np.asarray(t["W"], dtype=np.float64)).tobytes())
+            parts.append(b"" if t.get("t") is None else np.ascontiguousarray(np.asarray(t["t"], dtype=np.float64)).tobytes())
+        return hash(tuple(parts))
+
+    def _predict_plan(self, n):
+        """Captured n-step cascade, cached per (model, policy, reward, n) state: the reference rebuilds nothing
+        between calls either (tf.function), but here the cache is explicit -- any change of data, hyper-parameters,
+        policy parameters or reward parameters changes the key and rebuilds the plan (a few ms)."""
+        dyn = self.mgpr.device_gp()                       # (re)factorises only when data / hypers changed
+        key = (id(dyn), self.mgpr._cache_key, self.controller.state_key(), self._reward_key(), int(n))
+        cache = self.__dict__.setdefault("_plans", {})
+        hit = cache.get(int(n))
+        if hit is None or hit[0] != key:
+            terms, mult_mu = self.reward_spec()
+            plan = engine.PredictPlan(dyn, self.policy_spec(), terms, self.state_dim, int(n), mult_mu=mult_mu)
+            if len(cache) >= 8:
+                cache.clear()
+            cache[int(n)] = hit = (key, plan)
+        return hit[1]
+
     def predict(self, m_x, s_x, n):
-        """n-step cascade (pilco.py:118-136) -> (m [1,Ds], S [Ds,Ds], reward [1,1])."""
-        plan = self.rollout_plan(m_x, s_x, n)
-        traj_m, traj_S, reward = plan.forward()
-        if int(plan.info.max().item()):
-            raise RuntimeError("moment-matching rollout failed: covariance not positive definite")
-        return host(traj_m[0, -1:]), host(traj_S[0, -1]), host(reward.reshape(1, 1))
+        """n-step cascade (pilco.py:118-136) -> (m [1,Ds], S [Ds,Ds], reward [1,1]): one replay of a cached
+        CUDA graph (host moments in, host moments out)."""
+        from ..params import HostArray
+        M, S, rew = self._predict_plan(n)(m_x, s_x)
+        return M.view(HostArray), S.view(HostArray), rew.view(HostArray)
 
     def propagate(self, m_x, s_x):
         """one step (pilco.py:138-153) -> (M_x [1,Ds], S_x [Ds,Ds])"""

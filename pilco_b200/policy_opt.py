@@ -18,6 +18,7 @@ import torch
 from . import engine, controllers, _lib
 
 BIG = 1e10
+LAST_STATS = {}          # filled by optimize(): evaluator calls, restarts on this rank, horizon (bench.py reads it)
 
 
 class PolicyEvaluator:
@@ -37,6 +38,7 @@ class PolicyEvaluator:
             bf, Ds, U = c.policy_shapes
             spec = pilco.policy_spec(flat0)
             self.gp = spec["gp"]
+            self.ell_lower = float(c.models[0].kernel.lengthscales.transform.lower)
         self.shape = (Ds, U)
         terms, mult_mu = pilco.reward_spec()
         self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, terms,
@@ -90,7 +92,9 @@ class PolicyEvaluator:
             th = self.d_flat[:, bf * Ds + bf * U:].reshape(R, U, Ds)
             gp.X.copy_(self.d_flat[:, :bf * Ds].reshape(R, bf, Ds))
             gp.Y.copy_(self.d_flat[:, bf * Ds:bf * Ds + bf * U].reshape(R, bf, U))
-            gp.ell.copy_(1e-3 + torch.nn.functional.softplus(th))
+            # ell = lower + log(1 + e^theta): the controller's own transform (controllers.py:100), same formula as
+            # params.Softplus.forward on the host (np.logaddexp)
+            gp.ell.copy_(self.ell_lower + torch.logaddexp(th, torch.zeros_like(th)))
             engine.gp_refactorize(gp)
         plan.forward()
         g = plan.backward()
@@ -149,6 +153,7 @@ class LockstepLBFGS:
         threads = [threading.Thread(target=self._worker, args=(i,), daemon=True) for i in range(self.R)]
         for t in threads:
             t.start()
+        failure = None
         while True:
             with self.cv:
                 while any(self.active[i] and not self.pending[i] for i in range(self.R)):
@@ -156,7 +161,15 @@ class LockstepLBFGS:
                 if not any(self.active):
                     break
                 xs = self.x.copy()
-            loss, grad = self.evaluate(xs)                 # device work happens on this (main) thread
+            if failure is None:
+                try:
+                    loss, grad = self.evaluate(xs)             # device work happens on this (main) thread
+                except BaseException as exc:                   # noqa: BLE001 -- re-raised below, after the workers left
+                    failure = exc
+            if failure is not None:
+                # a failed evaluation (CUDA error, failed check) must not strand the workers in cv.wait():
+                # serve (BIG, 0) so that every SciPy instance terminates (flat objective), then re-raise
+                loss, grad = np.full(self.R, BIG), np.zeros_like(xs)
             with self.cv:
                 for i in range(self.R):
                     if self.pending[i]:
@@ -166,6 +179,8 @@ class LockstepLBFGS:
                 self.cv.notify_all()
         for t in threads:
             t.join()
+        if failure is not None:
+            raise failure
         if self.errors:
             raise self.errors[0]
         return self.final
@@ -237,6 +252,7 @@ def optimize(pilco, maxiter=50, restarts=1):
         finals = LockstepLBFGS(ev, flats0[mine], maxiter).run()
         xs = np.stack([f[1] for f in finals])
         loss, _ = ev(xs)                                   # rewards at the final points (pilco.py:96,103)
+        LAST_STATS.update(evals=int(ev.ncalls), restarts_local=len(mine), horizon=int(pilco.horizon))
         for k, r in enumerate(mine):
             local[r, 0] = loss[k]
             local[r, 1:] = xs[k]

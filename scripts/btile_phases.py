@@ -16,7 +16,7 @@ import bench                                   # noqa: E402
 from pilco_b200 import engine, _lib            # noqa: E402
 
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-wl = bench.make_workload()
+wl = bench.make_workload(bench.CONFIGS["metric"])
 gp = engine.gp_factorize(wl["X"], wl["Y"], wl["ell"], wl["sf2"], wl["sn2"])
 D, E = gp.D, gp.E
 rng = np.random.RandomState(0)

@@ -24,7 +24,15 @@ def test_reference_arm_prints_one_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     sys.path.insert(0, ROOT)
     import bench
-    assert line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    cfg = bench.CONFIGS["metric"]
+    assert line["metric"] == bench.metric_name(cfg) and line["unit"] == bench.UNIT
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
-    assert "N=300, E=10, H=40, fp64" in base["metric"] and "N=300, E=10, H=40, fp64" in bench.METRIC
-    assert bench.CFG["N"] == 300 and bench.CFG["Ds"] == 10 and bench.CFG["H"] == 40
+    assert "N=300, E=10, H=40, fp64" in base["metric"] and "N=300, E=10, H=40, fp64" in line["metric"]
+    assert cfg["N"] == 300 and cfg["Ds"] == 10 and cfg["H"] == 40
+    # the driver checks steps x ms_per_step against its own clock: they must be the run's real figures
+    assert line["steps"] == 1 and line["ms_per_step"] > 0
+    assert abs(line["value"] - line["rollout_steps_per_bench_step"] / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"]
+    # same workload string as our arm prints for this config
+    assert line["config"]["workload"] == bench.workload_string(cfg, cfg["R"])
+    # every BASELINE.json config has a bench shape
+    assert {"metric", "test_cascade", "inverted_pendulum", "inv_double_pendulum", "smgpr", "swimmer"} <= set(bench.CONFIGS)

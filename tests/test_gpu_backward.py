@@ -66,7 +66,7 @@ def test_mm_taped_matches_staged(n, D, E, mode, R):
     M, S, V, info, tape = engine.mm_forward_taped(gp, m, s)
     assert int(info.max().item()) == 0
     for got, ref in ((M, M0), (S, S0), (V, V0)):
-        assert scaled_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-11
+        assert scaled_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-9      # (summation order differs; S carries the trace term x |iK|)
     gm, gs = engine.mm_backward_taped(gp, m, s, M, gM, gS, gV, tape)
     for r in range(R):
         rm, rs = st.mm_backward_staged(X, ell, sf2, beta, iK, m[r], s[r], gM[r], gS[r], gV[r], mode)[:2]
