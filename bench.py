@@ -191,7 +191,7 @@ class CpuRollout:
         return float(total.detach())
 
     def steps_per_s(self, reps=2, h=4, grad=False, budget_s=30.0):
-        self.run(1, grad)                                   # warm-up
+        self.run(2 if grad else 1, grad)                    # warm-up (the reward of step 0 does not depend on the policy)
         t0 = time.perf_counter()
         done = 0
         for _ in range(reps):

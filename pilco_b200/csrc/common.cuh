@@ -194,7 +194,46 @@ static inline int pilco_current_device() {
     if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
     return d < PILCO_MAX_DEVICES ? d : PILCO_MAX_DEVICES - 1;
 }
-static inline int exp_table_upload() { return PILCO_OK; }       // (kept for the launchers: nothing to upload)
+static inline int exp_table_upload() { return PILCO_OK; }
+
+// ---------------------------------------------------------------------------------------------
+// Launch priorities.  A rollout step is a chain of ~15 small latency-bound kernels around one (or two) big tile
+// kernels; several sub-batches run on parallel streams so that one's chain overlaps another's tile pass.  The block
+// scheduler dispatches grids of EQUAL priority in arrival order, so a 4-CTA glue kernel queues behind every not yet
+// dispatched tile CTA of the other streams.  Glue kernels are therefore launched with the device's highest
+// priority (cudaLaunchAttributePriority; kept by graph capture): their CTAs take the next free slot.
+// PILCO_NO_PRIORITY=1 disables (A/B tuning switch).
+// ---------------------------------------------------------------------------------------------
+#include <stdlib.h>
+#include <utility>
+static inline int pilco_hi_priority() {
+    static int hi = 0x7fffffff;
+    if (hi == 0x7fffffff) {
+        int least = 0, greatest = 0;
+        const char* e = getenv("PILCO_NO_PRIORITY");
+        if (e && e[0] == '1') hi = 0;
+        else { cudaDeviceGetStreamPriorityRange(&least, &greatest); hi = greatest; }
+    }
+    return hi;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void launch_pri(bool hi, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = hi ? pilco_hi_priority() : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_hi(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    launch_pri(true, kern, grid, block, smem, st, std::forward<Args>(args)...);
+}
+// tile-type kernels: "glue" (high priority) while the whole grid fits the machine once, bulk work otherwise
+static inline bool pilco_small_grid(dim3 g) { return (long long)g.x * g.y * g.z < 296; }
+#endif       // (kept for the launchers: nothing to upload)
 
 __device__ __forceinline__ void exp_table_init(double* tab) {
     for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = g_exp_tab[j];

@@ -388,7 +388,7 @@ __global__ void fitc_axpy_kernel(int n, double* C, int ldc, long long cs, const 
 
 void chol_solve_vec_launch(cudaStream_t st, int batch, int n, const double* L, int ld, long long ms, int E,
                            const double* Y, long long Y_bs, long long y_es, int yinc, double* x, long long xs) {
-    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ld, ms, E, Y, Y_bs, y_es, yinc, x, xs);
+    launch_hi(chol_solve_vec_kernel, dim3(batch), dim3(256), n * sizeof(double), st, n, L, ld, ms, E, Y, Y_bs, y_es, yinc, x, xs);
 }
 
 extern "C" {
@@ -419,12 +419,12 @@ int pilco_gp_factorize(int n, int D, int E, int B,
     if (info) cudaMemsetAsync(info, 0, sizeof(int) * B, st);
     // K + sn2 I  (mgpr.py:82-84), zero outside n x n
     GramArgs g{n, n, D, E, X, X_bs, X, X_bs, ell, ell_bs, sf2, sf2_bs, sn2, sn2_bs, 0.0, L, ldw, ms, ldw, ldw, 0};
-    gram_kernel<<<dim3((ldw + 31) / 32, (ldw + 7) / 8, batch), dim3(32, 8), 0, st>>>(g);
+    launch_hi(gram_kernel, dim3((ldw + 31) / 32, (ldw + 7) / 8, batch), dim3(32, 8), 0, st, g);
     CUDA_LAUNCH_CHECK();
-    chol_kernel<<<batch, 256, 0, st>>>(n, L, ldw, ms, E, info);
+    launch_hi(chol_kernel, dim3(batch), dim3(256), 0, st, n, L, ldw, ms, E, info);
     CUDA_LAUNCH_CHECK();
     // beta = (L L^T)^-1 y_e   (mgpr.py:86-88)
-    chol_solve_vec_kernel<<<batch, 256, n * sizeof(double), st>>>(n, L, ldw, ms, E, Y, Y_bs, 1, E, beta, n);
+    launch_hi(chol_solve_vec_kernel, dim3(batch), dim3(256), n * sizeof(double), st, n, L, ldw, ms, E, Y, Y_bs, 1, E, beta, n);
     CUDA_LAUNCH_CHECK();
     if (iK) {
         // iK = L^-T L^-1 through the explicit triangular inverse (mgpr.py:85)
@@ -546,12 +546,12 @@ int pilco_fitc_factorize(int N, int Mi, int D, int E, const double* X, const dou
     cudaMemsetAsync(ws, 0, pilco_fitc_workspace_bytes(N, Mi, E), st);
     // Kmm + 1e-6 I  (smgpr.py:27), Kmn (smgpr.py:28)
     GramArgs gmm{Mi, Mi, D, E, Z, 0, Z, 0, ell, 0, sf2, 0, nullptr, 0, 1e-6, L, ldm, mm, ldm, ldm, 0};
-    gram_kernel<<<dim3((ldm + 31) / 32, (ldm + 7) / 8, E), dim3(32, 8), 0, st>>>(gmm);
+    launch_hi(gram_kernel, dim3((ldm + 31) / 32, (ldm + 7) / 8, E), dim3(32, 8), 0, st, gmm);
     CUDA_LAUNCH_CHECK();
     GramArgs gmn{Mi, N, D, E, Z, 0, X, 0, ell, 0, sf2, 0, nullptr, 0, 0.0, Vg, ldn, mn, Mi, N, 0};
-    gram_kernel<<<dim3((N + 31) / 32, (Mi + 7) / 8, E), dim3(32, 8), 0, st>>>(gmn);     // Kmn -> Vg (temp)
+    launch_hi(gram_kernel, dim3((N + 31) / 32, (Mi + 7) / 8, E), dim3(32, 8), 0, st, gmn);     // Kmn -> Vg (temp)
     CUDA_LAUNCH_CHECK();
-    chol_kernel<<<E, 256, 0, st>>>(Mi, L, ldm, mm, E, info);                            // L = chol(Kmm)  :29
+    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, Mi, L, ldm, mm, E, info);                            // L = chol(Kmm)  :29
     CUDA_LAUNCH_CHECK();
     int rc = tri_inverse(st, E, Mi, L, ldm, mm, Linv, ldm, mm, T, mm);                   // Linv = L^-1
     if (rc) return rc;
@@ -563,7 +563,7 @@ int pilco_fitc_factorize(int N, int Mi, int D, int E, const double* X, const dou
     if (rc) return rc;
     add_diag_kernel<<<dim3((Mi + 127) / 128, E), 128, 0, st>>>(Mi, Am, ldm, mm, sn2);    // + sn2 I   :34-35
     CUDA_LAUNCH_CHECK();
-    chol_kernel<<<E, 256, 0, st>>>(Mi, Am, ldm, mm, E, info);                           // Am
+    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, Mi, Am, ldm, mm, E, info);                           // Am
     CUDA_LAUNCH_CHECK();
     fill(st, T, (size_t)E * mm, 0.0);
     rc = tri_inverse(st, E, Mi, Am, ldm, mm, Aminv, ldm, mm, T, mm);                     // Am^-1

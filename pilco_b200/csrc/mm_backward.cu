@@ -488,9 +488,9 @@ static int launch_btile(const MMBwdParams& bp, cudaStream_t st) {
         configured = true;
     }
     const int E = bp.f.gp.E;
-    mm_btile_kernel<KS, false><<<dim3(bp.B.F.NB, bp.B.P2, bp.f.R), 256, smem, st>>>(bp);
+    { const dim3 gb(bp.B.F.NB, bp.B.P2, bp.f.R); launch_pri(pilco_small_grid(gb), mm_btile_kernel<KS, false>, gb, dim3(256), smem, st, bp); }
     if (bp.f.gp.mode == 0 && bp.f.gp.iK != nullptr)
-        mm_btile_kernel<KS, true><<<dim3(bp.B.F.NB, E, bp.f.R), 256, smem, st>>>(bp);
+        { const dim3 gb(bp.B.F.NB, E, bp.f.R); launch_pri(pilco_small_grid(gb), mm_btile_kernel<KS, true>, gb, dim3(256), smem, st, bp); }
     return PILCO_OK;
 }
 
@@ -519,13 +519,13 @@ int mm_backward_launch(MMBwdParams bp, cudaStream_t st) {
     CUDA_LAUNCH_CHECK();
     dim3 gf(E + E * E, R);
     switch (ks) {
-        case 1: mm_bfinish_kernel<4><<<gf, 128, 0, st>>>(bp); break;
-        case 2: mm_bfinish_kernel<8><<<gf, 128, 0, st>>>(bp); break;
-        case 3: mm_bfinish_kernel<12><<<gf, 128, 0, st>>>(bp); break;
-        default: mm_bfinish_kernel<16><<<gf, 128, 0, st>>>(bp); break;
+        case 1: launch_hi(mm_bfinish_kernel<4>, dim3(gf), dim3(128), 0, st, bp); break;
+        case 2: launch_hi(mm_bfinish_kernel<8>, dim3(gf), dim3(128), 0, st, bp); break;
+        case 3: launch_hi(mm_bfinish_kernel<12>, dim3(gf), dim3(128), 0, st, bp); break;
+        default: launch_hi(mm_bfinish_kernel<16>, dim3(gf), dim3(128), 0, st, bp); break;
     }
     CUDA_LAUNCH_CHECK();
-    mm_breduce_kernel<<<R, 128, 0, st>>>(bp);
+    launch_hi(mm_breduce_kernel, dim3(R), dim3(128), 0, st, bp);
     CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }

@@ -43,9 +43,10 @@ static int launch_tile(const MMParams& p, cudaStream_t st) {
     if (rpc_env > 0) rpc = rpc_env;
     if (rpc > p.L.NB) rpc = p.L.NB;
     dim3 grid((p.L.NB + rpc - 1) / rpc, p.L.P, p.R);
-    if (variant == 2) mm_tile_kernel<KS, 4><<<grid, 256, smem, st>>>(p, rpc);
-    else if (variant == 1) mm_tile_kernel<KS, 3><<<grid, 256, smem, st>>>(p, rpc);
-    else mm_tile_kernel<KS, 2><<<grid, 256, smem, st>>>(p, rpc);
+    const bool hi = pilco_small_grid(grid);          // e.g. the RBF policy's 3 pairs: glue, not bulk work
+    if (variant == 2) launch_pri(hi, mm_tile_kernel<KS, 4>, grid, dim3(256), smem, st, p, rpc);
+    else if (variant == 1) launch_pri(hi, mm_tile_kernel<KS, 3>, grid, dim3(256), smem, st, p, rpc);
+    else launch_pri(hi, mm_tile_kernel<KS, 2>, grid, dim3(256), smem, st, p, rpc);
     return PILCO_OK;
 }
 
@@ -70,7 +71,7 @@ int mm_forward_launch(const MMParams& p, cudaStream_t st, bool with_finish) {
     if (rc) return rc;
     CUDA_LAUNCH_CHECK();
     if (with_finish) {
-        mm_finish_kernel<<<p.R, 128, 0, st>>>(p);
+        launch_hi(mm_finish_kernel, dim3(p.R), dim3(128), 0, st, p);
         CUDA_LAUNCH_CHECK();
     }
     return PILCO_OK;
@@ -124,7 +125,7 @@ static int mm_forward_profile(MMParams& p, float* ms_out, cudaStream_t st) {
         default: rc = launch_tile<4>(p, st); break;
     }
     cudaEventRecord(ev[2], st);
-    mm_finish_kernel<<<p.R, 128, 0, st>>>(p);
+    launch_hi(mm_finish_kernel, dim3(p.R), dim3(128), 0, st, p);
     cudaEventRecord(ev[3], st);
     cudaEventSynchronize(ev[3]);
     for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);

@@ -528,8 +528,8 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
 template <int DP, bool BWD>
 static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
     const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
-    mm_setup1_kernel<DP, BWD><<<dim3((ntask + SETUP_WARPS - 1) / SETUP_WARPS, p.R), 32 * SETUP_WARPS, 0, st>>>(p);
-    mm_setup2_kernel<DP, BWD><<<dim3(ntask, p.R), 128, 0, st>>>(p);
+    launch_hi(mm_setup1_kernel<DP, BWD>, dim3((ntask + SETUP_WARPS - 1) / SETUP_WARPS, p.R), dim3(32 * SETUP_WARPS), 0, st, p);
+    launch_hi(mm_setup2_kernel<DP, BWD>, dim3(ntask, p.R), dim3(128), 0, st, p);
 }
 
 // -------------------------------------------------------------------------------------------------

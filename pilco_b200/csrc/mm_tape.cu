@@ -3,18 +3,32 @@
 // autodiff through mgpr.py:91-149); numpy statement of exactly these formulas: oracle/staged.py:mm_backward_tape.
 #include "mm_tape.cuh"
 
+#include <stdlib.h>
+
 template <int KS>
 static int launch_tape_tile(const MMParams& p, cudaStream_t st) {
     static bool configured_dev[PILCO_MAX_DEVICES] = {false};      // function attributes are per device
+    static int variant = 1;        // 0: <=128 regs; 1: <=96 regs, 2 CTAs/SM; 2: <=80 regs, 2 CTAs/SM (padded smem); 3: <=80 regs, 3 CTAs/SM
     bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {
+        const char* e = getenv("PILCO_TAPE_VARIANT");           // tuning switch
+        if (e && e[0] >= '0' && e[0] <= '3') variant = e[0] - '0';
         const int big = (int)mm_tape_smem_bytes(TAPE_MAX_NP, 20);
-        if (cudaFuncSetAttribute(mm_tape_tile_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+            cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 304>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+            cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 352>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)
+            return PILCO_ERR_LAUNCH;
         configured = true;
     }
     if (p.L.np > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
-    const size_t smem = mm_tape_smem_bytes(p.L.np, p.L.ldz);
-    mm_tape_tile_kernel<KS><<<dim3(p.TL.cs, p.L.P, p.R), 256, smem, st>>>(p);
+    size_t smem = mm_tape_smem_bytes(p.L.np, p.L.ldz);
+    const dim3 grid(p.TL.cs, p.L.P, p.R);
+    if (variant == 0) mm_tape_tile_kernel<KS, 256><<<grid, 256, smem, st>>>(p);
+    else if (variant == 1) mm_tape_tile_kernel<KS, 304><<<grid, 256, smem, st>>>(p);
+    else {
+        if (variant == 2 && smem < 80 * 1024) smem = 80 * 1024;    // 2 CTAs per SM
+        mm_tape_tile_kernel<KS, 352><<<grid, 256, smem, st>>>(p);
+    }
     return PILCO_OK;
 }
 
@@ -170,34 +184,50 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
     for (int i = 0; i < NSYMT; ++i) { cu[i][0] = cu[i][1] = cv[i][0] = cv[i][1] = 0.0; }
 #pragma unroll
     for (int i = 0; i < TX * TX; ++i) { ch[i][0] = ch[i][1] = 0.0; }
+    // TBU k-steps per trip: all their operands are loaded first (the tape was written a whole rollout ago and comes
+    // from DRAM -- the loads of a trip are independent, so their latencies overlap), then the DMMAs run
+    constexpr int TBU = (TX <= 2) ? 4 : 2;
     const int nks = (n + 3) >> 2;
-    for (int ks = warp; ks < nks; ks += TB_WARPS) {
-        const int row = 4 * ks + t;
-        const bool live = row < n;
-        const double u = su[row], v = sv[row];                  // (0 beyond n: su/sv are np long, np >= 4 nks)
-        double zx[TX], bu[TX], bv[TX], bh[TX];
+    for (int ks0 = warp; ks0 < nks; ks0 += TB_WARPS * TBU) {
+        double zx[TBU][TX], bh[TBU][TX], uu[TBU], vv[TBU];
 #pragma unroll
-        for (int tl = 0; tl < TX; ++tl) {
-            const int c = g + 8 * tl;
-            double z = 0.0, h = 0.0;
-            if (live) {
-                if (c < D) { z = X[(size_t)row * D + c] - sm[c]; if (HZg) h = HZg[(size_t)row * TL.ldh + c]; }
-                else if (c == D) z = 1.0;
-            }
-            zx[tl] = z; bu[tl] = u * z; bv[tl] = v * z; bh[tl] = h;
-        }
-        int si = 0;
+        for (int k = 0; k < TBU; ++k) {
+            const int row = 4 * (ks0 + k * TB_WARPS) + t;
+            const bool live = row < n;                            // (also false for k-steps beyond nks)
+            uu[k] = live ? su[row] : 0.0; vv[k] = live ? sv[row] : 0.0;
 #pragma unroll
-        for (int mt = 0; mt < TX; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < TX; ++nt) {
-                if (nt >= mt) {
-                    dmma884(cu[si][0], cu[si][1], zx[mt], bu[nt]);
-                    dmma884(cv[si][0], cv[si][1], zx[mt], bv[nt]);
-                    ++si;
+            for (int tl = 0; tl < TX; ++tl) {
+                const int c = g + 8 * tl;
+                double z = 0.0, h = 0.0;
+                if (live) {
+                    if (c < D) { z = X[(size_t)row * D + c]; if (HZg) h = HZg[(size_t)row * TL.ldh + c]; }
+                    else if (c == D) z = 1.0;
                 }
-                if (!is_out) dmma884(ch[mt * TX + nt][0], ch[mt * TX + nt][1], zx[mt], bh[nt]);
+                zx[k][tl] = z; bh[k][tl] = h;
             }
+        }
+#pragma unroll
+        for (int k = 0; k < TBU; ++k) {
+            double bu[TX], bv[TX];
+#pragma unroll
+            for (int tl = 0; tl < TX; ++tl) {
+                const int c = g + 8 * tl;
+                if (c < D) zx[k][tl] -= sm[c];                    // (a dead row has z = 0 and u = v = h = 0: no contribution)
+                bu[tl] = uu[k] * zx[k][tl]; bv[tl] = vv[k] * zx[k][tl];
+            }
+            int si = 0;
+#pragma unroll
+            for (int mt = 0; mt < TX; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < TX; ++nt) {
+                    if (nt >= mt) {
+                        dmma884(cu[si][0], cu[si][1], zx[k][mt], bu[nt]);
+                        dmma884(cv[si][0], cv[si][1], zx[k][mt], bv[nt]);
+                        ++si;
+                    }
+                    if (!is_out) dmma884(ch[mt * TX + nt][0], ch[mt * TX + nt][1], zx[k][mt], bh[k][nt]);
+                }
+        }
     }
     // cross-warp reduction (fixed order), then warp 0 scatters the C fragments into square matrices
     if (warp > 0) {
@@ -330,14 +360,14 @@ int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_redu
         configured = true;
     }
     switch (ksteps_of(bp.gp.D)) {
-        case 1: mm_tape_bfinish_kernel<4><<<gf, TB_THREADS, smem, st>>>(bp); break;
-        case 2: mm_tape_bfinish_kernel<8><<<gf, TB_THREADS, smem, st>>>(bp); break;
-        case 3: mm_tape_bfinish_kernel<12><<<gf, TB_THREADS, smem, st>>>(bp); break;
-        default: mm_tape_bfinish_kernel<16><<<gf, TB_THREADS, smem, st>>>(bp); break;
+        case 1: launch_hi(mm_tape_bfinish_kernel<4>, dim3(gf), dim3(TB_THREADS), smem, st, bp); break;
+        case 2: launch_hi(mm_tape_bfinish_kernel<8>, dim3(gf), dim3(TB_THREADS), smem, st, bp); break;
+        case 3: launch_hi(mm_tape_bfinish_kernel<12>, dim3(gf), dim3(TB_THREADS), smem, st, bp); break;
+        default: launch_hi(mm_tape_bfinish_kernel<16>, dim3(gf), dim3(TB_THREADS), smem, st, bp); break;
     }
     CUDA_LAUNCH_CHECK();
     if (with_reduce) {
-        mm_tape_breduce_kernel<<<R, 128, 0, st>>>(bp);
+        launch_hi(mm_tape_breduce_kernel, dim3(R), dim3(128), 0, st, bp);
         CUDA_LAUNCH_CHECK();
     }
     return PILCO_OK;

@@ -243,8 +243,11 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
     }
 }
 
-template <int KS>
-__global__ void __launch_bounds__(256, 2) mm_tape_tile_kernel(MMParams p) {
+// LB = the thread count promised to the compiler (the launch uses 256): with 2 CTAs per SM it caps the registers at
+// 65536 / (2 LB) -- 304 -> 96 registers (2 CTAs/SM leave 16 k registers per SM for the latency-bound glue kernels of
+// the other sub-batches to run BESIDE the tile CTAs), 352 -> 80 registers (3 CTAs/SM fit).  No variant spills.
+template <int KS, int LB>
+__global__ void __launch_bounds__(LB, 2) mm_tape_tile_kernel(MMParams p) {
     int a, b;
     pair_decode(blockIdx.y, a, b);
     if (a == b && p.gp.mode == 0 && p.gp.iK != nullptr) mm_tape_body<KS, true>(p);

@@ -221,13 +221,13 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
             d.dyn_prev = dyn_params(0);
         }
         if (ro->pol.kind == PILCO_POLICY_RBF && t < H) d.pol = pol_params(t); else d.pol = d.dyn_prev;
-        ro_state_kernel<<<R, 128, 0, st>>>(d);
+        launch_hi(ro_state_kernel, dim3(R), dim3(128), 0, st, d);
         CUDA_LAUNCH_CHECK();
         if (t == H) break;
         if (ro->pol.kind == PILCO_POLICY_RBF) {
             rc = mm_forward_launch(d.pol, st, false);
             if (rc) return rc;
-            ro_policy_kernel<<<R, 128, 0, st>>>(d);
+            launch_hi(ro_policy_kernel, dim3(R), dim3(128), 0, st, d);
             CUDA_LAUNCH_CHECK();
         }
         rc = mm_forward_launch(dyn_params(t), st, false);

@@ -277,7 +277,7 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
         d.Mp = slot(FL.Mp, U, t); d.Sp = slot(FL.Sp, (size_t)U * U, t); d.Vp = slot(FL.Vp, (size_t)Ds * U, t);
         d.Mu = slot(FL.Mu, U, t); d.Su = slot(FL.Su, (size_t)U * U, t); d.Cq = slot(FL.Cq, (size_t)U * U, t);
         d.Vu = slot(FL.Vu, (size_t)Ds * U, t);
-        rb_pre_kernel<<<R, 128, 0, st>>>(d);
+        launch_hi(rb_pre_kernel, dim3(R), dim3(128), 0, st, d);
         CUDA_LAUNCH_CHECK();
         if (ro->tape) {                              // consume the tape of step t: no exponential is recomputed
             MMTapeBwd tb;
@@ -296,7 +296,7 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
             rc = mm_backward_launch(bp, st);
         }
         if (rc) return rc;
-        rb_post_kernel<<<R, 128, 0, st>>>(d);
+        launch_hi(rb_post_kernel, dim3(R), dim3(128), 0, st, d);
         CUDA_LAUNCH_CHECK();
         if (rbf) {
             MMBwdParams pp = mm_bwd_params(&ro->pol.rbf, R, ro->traj_m + (size_t)t * Ds, (long long)(H + 1) * Ds,
@@ -313,7 +313,7 @@ int pilco_rollout_backward(const pilco_rollout* ro, const pilco_rollout_grad* g,
         const int ldw = pad64(bf);
         chol_solve_vec_launch(st, R * U, bf, g->pol_L, ldw, (long long)ldw * ldw, U,
                               buf(BL.gbeta), (long long)U * bf, bf, 1, buf(BL.gy), bf);
-        rbf_factor_bwd_kernel<<<R, 128, 0, st>>>(bf, Ds, U, ro->pol.rbf.X, ro->pol.rbf.ell, ro->pol.rbf.sf2, ro->pol.rbf.sf2_bs,
+        launch_hi(rbf_factor_bwd_kernel, dim3(R), dim3(128), 0, st, bf, Ds, U, ro->pol.rbf.X, ro->pol.rbf.ell, ro->pol.rbf.sf2, ro->pol.rbf.sf2_bs,
                                                   ro->pol.rbf.beta,
                                                   buf(BL.gy), g->gXc, g->gYc, g->gell);
         CUDA_LAUNCH_CHECK();
