@@ -113,6 +113,20 @@ int pilco_gp_factorize(int n, int D, int E, int B,
                        int* info,                            /* [B] or NULL */
                        void* ws, size_t ws_bytes, pilco_stream_t stream);
 
+/* Incremental set_data: k rows appended to the data of a factorised model with UNCHANGED
+ * hyper-parameters (pilco/models/mgpr.py:38-45; examples/inv_double_pendulum.py:102-103, swimmer.py:87-88 append the
+ * rows of each new episode).  X [n0+k, D] and Y [n0+k, E] hold the old rows first; iK_old [E,ldk_old,ldk_old] is the
+ * inverse pilco_gp_factorize / an earlier append produced.  Writes the new zero-padded inverse iK_new
+ * [E,ldk_new,ldk_new] (ldk_new >= pilco_pad_n(n0+k), out of place) and beta_new [E,n0+k] by the block-inverse
+ * (Schur complement) update: O(n^2 k) instead of O(n^3).  info[0] bit 1: Schur complement not positive definite. */
+size_t pilco_gp_append_workspace_bytes(int n0, int k, int E);
+int pilco_gp_append(int n0, int k, int D, int E,
+                    const double* X, const double* Y,
+                    const double* ell, const double* sf2, const double* sn2,
+                    const double* iK_old, int ldk_old,
+                    double* iK_new, int ldk_new, double* beta_new, int* info,
+                    void* ws, size_t ws_bytes, pilco_stream_t stream);
+
 /* GP training objective: nlml[b,e] = -log p(y_e | X, theta_be) and its gradient w.r.t. the
  * constrained hyper-parameters, batched over B hyper-parameter sets x E outputs.  Replaces
  * gpflow.models.GPR.training_loss + TF autodiff inside MGPR.optimize (pilco/models/mgpr.py:47-75); the Gamma priors

@@ -217,14 +217,32 @@ static inline int pilco_hi_priority() {
     return hi;
 }
 #ifdef __CUDACC__
+// Programmatic dependent launch: every kernel launched through launch_pri starts with pdl_wait() (griddepcontrol.wait:
+// returns once the preceding grid in the stream has completed and its memory is visible) followed by pdl_trigger()
+// (lets the NEXT grid's CTAs be scheduled early; they park in their own pdl_wait).  With the stream-serialisation
+// attribute the launch latency and grid drain/fill gaps between the ~15 dependent kernels of a rollout step overlap
+// instead of adding up.  Stream capture turns these into programmatic graph edges.
+// MEASURED (round 2): no latency gain at R = 1 (45.3 -> 44.8 us per step) and 5-7 % LOWER throughput at R = 32 (the
+// early-scheduled CTAs of the dependents hold SM resources the tile kernels of the other sub-batches could use), so
+// it is OFF by default; PILCO_PDL=1 enables it (the device-side instructions are no-ops without the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define PDL_ENTRY() do { pdl_wait(); pdl_trigger(); } while (0)
+static inline int pilco_use_pdl() {
+    static int use = -1;
+    if (use < 0) { const char* e = getenv("PILCO_PDL"); use = (e && e[0] == '1') ? 1 : 0; }
+    return use;
+}
 template <typename... KArgs, typename... Args>
 static inline void launch_pri(bool hi, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributePriority;
     at[0].val.priority = hi ? pilco_hi_priority() : 0;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pilco_use_pdl() ? 2 : 1;
     cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 template <typename... KArgs, typename... Args>

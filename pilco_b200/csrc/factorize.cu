@@ -27,6 +27,7 @@ struct GramArgs {
 };
 
 __global__ void __launch_bounds__(256) gram_kernel(GramArgs g) {
+    PDL_ENTRY();
     const int z = blockIdx.z, bidx = z / g.E, e = z % g.E;
     const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
     if (i >= g.rows_out || j >= g.cols_out) return;
@@ -51,6 +52,7 @@ __global__ void __launch_bounds__(256) gram_kernel(GramArgs g) {
 // Only the lower triangle is meaningful on exit.  info[b] |= 2 if a pivot is not positive.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) chol_kernel(int n, double* Aall, int ld, long long ms, int mats_per_b, int* info) {
+    PDL_ENTRY();
     __shared__ double sD[FB][FB + 1];
     __shared__ double sPi[64][FB + 1];
     __shared__ double sPj[64][FB + 1];
@@ -292,6 +294,7 @@ __global__ void __launch_bounds__(256) chol_solve_vec_kernel(int n, const double
                                                              int E, const double* Y, long long Y_bs,
                                                              long long y_es, int yinc,
                                                              double* xall, long long xs) {
+    PDL_ENTRY();
     extern __shared__ double sx[];            // n doubles
     __shared__ double sD[FB][FB + 1];
     const double* L = Lall + (size_t)blockIdx.x * ms;
@@ -435,6 +438,100 @@ int pilco_gp_factorize(int n, int D, int E, int B,
         rc = gemm(st, batch, n, n, n, 1, 0, 1.0, Xi, ldw, ms, Xi, ldw, ms, 0.0, iK, ldk, (long long)ldk * ldk);
         if (rc) return rc;
     }
+    return PILCO_OK;
+}
+
+// ---- incremental set_data: k rows appended to a factorised model, hyper-parameters unchanged -------------------
+// (pilco/models/mgpr.py:38-45 swaps the data, examples/inv_double_pendulum.py:102-103 and
+// swimmer.py:87-88 append the T rows of every new episode).  Block inverse of A1 = [[A0, K12], [K21, K22 + sn2 I]]:
+//   F = K21 A0^-1,  S = K22 + sn2 I - F K12 (Schur complement, k x k, SPD),  G = S^-1 F,
+//   A1^-1 = [[A0^-1 + F' G, -G'], [-G, S^-1]],   beta = A1^-1 y.
+// O(n^2 k) instead of O(n^3); only the old inverse is needed (no Cholesky factor of the old matrix).
+__global__ void __launch_bounds__(256) append_assemble_kernel(int n0, int k, const double* G, int ldg, long long gs,
+                                                              const double* Sinv, int lds, long long ss,
+                                                              double* iK, int ldk, long long ks) {
+    PDL_ENTRY();
+    const int e = blockIdx.y;
+    const int n1 = n0 + k;
+    const double* Ge = G + (size_t)e * gs;
+    const double* Se = Sinv + (size_t)e * ss;
+    double* O = iK + (size_t)e * ks;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < (size_t)k * n1; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / n1), j = (int)(idx % n1);          // row n0 + i of the new inverse
+        if (j < n0) {
+            const double v = -Ge[(size_t)i * ldg + j];
+            O[(size_t)(n0 + i) * ldk + j] = v;
+            O[(size_t)j * ldk + n0 + i] = v;
+        } else {
+            O[(size_t)(n0 + i) * ldk + j] = Se[(size_t)i * lds + (j - n0)];
+        }
+    }
+}
+
+extern "C" size_t pilco_gp_append_workspace_bytes(int n0, int k, int E) {
+    if (n0 < 1 || k < 1 || E < 1) return 0;
+    const size_t ld0 = pad64(n0), kp = pad64(k);
+    // K21, F, G: [kp x ld0] each; S, L^-1, S^-1: [kp x kp]; T: [FB x kp]
+    return (size_t)E * (3 * kp * ld0 + 3 * kp * kp + FB * kp) * sizeof(double);
+}
+
+extern "C" int pilco_gp_append(int n0, int k, int D, int E,
+                               const double* X, const double* Y,            /* [n0+k, D], [n0+k, E]: old rows first */
+                               const double* ell, const double* sf2, const double* sn2,
+                               const double* iK_old, int ldk_old,
+                               double* iK_new, int ldk_new, double* beta_new, int* info,
+                               void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    if (!X || !Y || !ell || !sf2 || !sn2 || !iK_old || !iK_new || !beta_new || !ws) return PILCO_ERR_NULL;
+    if (n0 < 1 || k < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE) return PILCO_ERR_DIM;
+    const int n1 = n0 + k;
+    if (ldk_old < pad64(n0) || ldk_new < pad64(n1)) return PILCO_ERR_DIM;
+    if (iK_old == iK_new) return PILCO_ERR_DIM;                             // out of place (leading dimensions may differ)
+    if (ws_bytes < pilco_gp_append_workspace_bytes(n0, k, E)) return PILCO_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ld0 = pad64(n0), kp = pad64(k);
+    const long long rs = (long long)kp * ld0, qs = (long long)kp * kp;
+    double* K21 = (double*)ws;
+    double* F = K21 + (size_t)E * rs;
+    double* G = F + (size_t)E * rs;
+    double* S = G + (size_t)E * rs;
+    double* Li = S + (size_t)E * qs;
+    double* Si = Li + (size_t)E * qs;
+    double* T = Si + (size_t)E * qs;
+    const double* Xn = X + (size_t)n0 * D;
+    if (info) cudaMemsetAsync(info, 0, sizeof(int), st);
+    // K21 = k(Xnew, Xold) [k x n0];  S = k(Xnew, Xnew) + sn2 I
+    GramArgs g1{k, n0, D, E, Xn, 0, X, 0, ell, 0, sf2, 0, nullptr, 0, 0.0, K21, ld0, rs, k, n0, 0};
+    launch_hi(gram_kernel, dim3((n0 + 31) / 32, (k + 7) / 8, E), dim3(32, 8), 0, st, g1);
+    GramArgs g2{k, k, D, E, Xn, 0, Xn, 0, ell, 0, sf2, 0, sn2, 0, 0.0, S, kp, qs, kp, kp, 0};
+    launch_hi(gram_kernel, dim3((kp + 31) / 32, (kp + 7) / 8, E), dim3(32, 8), 0, st, g2);
+    CUDA_LAUNCH_CHECK();
+    const long long ko = (long long)ldk_old * ldk_old, kn = (long long)ldk_new * ldk_new;
+    int rc = gemm(st, E, k, n0, n0, 0, 0, 1.0, K21, ld0, rs, iK_old, ldk_old, ko, 0.0, F, ld0, rs);          // F = K21 A0^-1
+    if (rc) return rc;
+    rc = gemm(st, E, k, k, n0, 0, 1, -1.0, F, ld0, rs, K21, ld0, rs, 1.0, S, kp, qs);                        // S -= F K12
+    if (rc) return rc;
+    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, k, S, kp, qs, E, info);
+    CUDA_LAUNCH_CHECK();
+    cudaMemsetAsync(Li, 0, (size_t)E * qs * sizeof(double), st);
+    rc = tri_inverse(st, E, k, S, kp, qs, Li, kp, qs, T, (long long)FB * kp);
+    if (rc) return rc;
+    rc = gemm(st, E, k, k, k, 1, 0, 1.0, Li, kp, qs, Li, kp, qs, 0.0, Si, kp, qs);                           // S^-1 = L^-T L^-1
+    if (rc) return rc;
+    rc = gemm(st, E, k, n0, k, 0, 0, 1.0, Si, kp, qs, F, ld0, rs, 0.0, G, ld0, rs);                          // G = S^-1 F
+    if (rc) return rc;
+    // new inverse: zero padded [ldk_new x ldk_new]; old block copied, then + F' G; then the border blocks
+    cudaMemsetAsync(iK_new, 0, (size_t)E * kn * sizeof(double), st);
+    for (int e = 0; e < E; ++e)
+        cudaMemcpy2DAsync(iK_new + (size_t)e * kn, (size_t)ldk_new * sizeof(double), iK_old + (size_t)e * ko,
+                          (size_t)ldk_old * sizeof(double), (size_t)n0 * sizeof(double), n0, cudaMemcpyDeviceToDevice, st);
+    rc = gemm(st, E, n0, n0, k, 1, 0, 1.0, F, ld0, rs, G, ld0, rs, 1.0, iK_new, ldk_new, kn);
+    if (rc) return rc;
+    launch_hi(append_assemble_kernel, dim3((unsigned)min((size_t)256, ((size_t)k * n1 + 255) / 256), E), dim3(256), 0, st,
+              n0, k, (const double*)G, ld0, rs, (const double*)Si, kp, qs, iK_new, ldk_new, kn);
+    CUDA_LAUNCH_CHECK();
+    // beta = A1^-1 y_e  (row e of beta [E, n1]; y_e = column e of Y)
+    matvec_kernel<<<dim3(n1, E), 32, 0, st>>>(n1, n1, 0, iK_new, ldk_new, kn, Y, 1, E, beta_new, n1);
+    CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }
 

@@ -21,6 +21,7 @@ static inline __host__ __device__ size_t mm_btile_smem_bytes(int np, int ldz) {
 // DIAG = false: grid (NB, E*E, R), every other ordered pair (CTAs of (a,a) pairs that DIAG handles exit at once).
 template <int KS, bool DIAG>
 __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams bp) {
+    PDL_ENTRY();
     constexpr int DP = 4 * KS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const MMParams& p = bp.f;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
 
 template <int DP>
 __global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
+    PDL_ENTRY();
     const MMParams& p = bp.f;
     const pilco_gp_model& gp = p.gp;
     const MMBws& B = bp.B;
@@ -422,6 +424,7 @@ __global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
 // reduce: sum task partials
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) mm_breduce_kernel(MMBwdParams bp) {
+    PDL_ENTRY();
     const MMParams& p = bp.f;
     const pilco_gp_model& gp = p.gp;
     const MMBws& B = bp.B;

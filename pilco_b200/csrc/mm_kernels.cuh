@@ -124,39 +124,27 @@ __device__ __forceinline__ void chol_solve_regs(const double* __restrict__ Ls, c
 }
 
 // stage 1: the serial part of every task (one warp per task): D x D Cholesky + solves -> matrices in workspace
-template <int DP, bool BWD>
-__global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p) {
-    const int r = blockIdx.y;
-    const pilco_gp_model& gp = p.gp;
-    const int D = gp.D, E = gp.E;
-    const MMWs& L = p.L;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ntask = BWD ? L.P : E + L.P;
-    const int task0 = blockIdx.x * SETUP_WARPS + warp;
-    const int task = BWD ? task0 + E : task0;                  // BWD: pair tasks only (ordered pairs)
-
-    __shared__ double s_s[MAXD * SLD];                         // symmetrised input covariance (all warps)
-    __shared__ double sLw[SETUP_WARPS][MAXD * SLD];            // per warp: Cholesky factor
-    __shared__ double sQw[SETUP_WARPS][MAXD * SLD];            // per warp: raw Q
-    __shared__ double spw[SETUP_WARPS][3][MAXD];
-
-    const double* ell = gp.ell + (size_t)r * gp.ell_bs;
-    const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
+// symmetrised input covariance of restart r -> s_s [DP][SLD] (all threads of the CTA; caller synchronises)
+template <int DP>
+__device__ __forceinline__ void setup_stage_s(const MMParams& p, int r, double* s_s) {
+    const int D = p.gp.D;
     const double* sr = p.s + (size_t)r * p.s_rs;
-    double* wsr = p.ws + (size_t)r * L.per_r;
-
-    for (int e = tid; e < DP * DP; e += blockDim.x) {
+    for (int e = threadIdx.x; e < DP * DP; e += blockDim.x) {
         const int i = e / DP, j = e % DP;
         s_s[i * SLD + j] = (i < D && j < D) ? 0.5 * (sr[i * D + j] + sr[j * D + i]) : 0.0;
     }
-    __syncthreads();
-    if (task0 >= ntask) return;
+}
 
-    double* Ls = sLw[warp];
-    double* Qs = sQw[warp];
-    double* pa = spw[warp][0];
-    double* pb = spw[warp][1];
-    double* dinv = spw[warp][2];
+// stage 1 of ONE task by ONE warp (scratch Ls, Qs [MAXD*SLD], pa, pb, dinv [MAXD] private to the warp)
+template <int DP, bool BWD>
+__device__ __forceinline__ void mm_setup1_task(const MMParams& p, int r, int task, int lane, const double* s_s,
+                                               double* Ls, double* Qs, double* pa, double* pb, double* dinv) {
+    const pilco_gp_model& gp = p.gp;
+    const int D = gp.D, E = gp.E;
+    const MMWs& L = p.L;
+    const double* ell = gp.ell + (size_t)r * gp.ell_bs;
+    const double* sf2 = gp.sf2 + (size_t)r * gp.sf2_bs;
+    double* wsr = p.ws + (size_t)r * L.per_r;
     const int li = lane < DP ? lane : DP - 1;                  // clamp so idle lanes read valid memory
 
     if (!BWD && task < E) {
@@ -262,6 +250,25 @@ __global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p)
     }
 }
 
+// stage 1 as its own launch (ordered-pair backward mode; forward mode uses mm_setup_fused_kernel)
+template <int DP, bool BWD>
+__global__ void __launch_bounds__(32 * SETUP_WARPS) mm_setup1_kernel(MMParams p) {
+    PDL_ENTRY();
+    const int r = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
+    const int task0 = blockIdx.x * SETUP_WARPS + warp;
+    const int task = BWD ? task0 + p.gp.E : task0;             // BWD: pair tasks only (ordered pairs)
+    __shared__ double s_s[MAXD * SLD];                         // symmetrised input covariance (all warps)
+    __shared__ double sLw[SETUP_WARPS][MAXD * SLD];            // per warp: Cholesky factor
+    __shared__ double sQw[SETUP_WARPS][MAXD * SLD];            // per warp: raw Q
+    __shared__ double spw[SETUP_WARPS][3][MAXD];
+    setup_stage_s<DP>(p, r, s_s);
+    __syncthreads();
+    if (task0 >= ntask) return;
+    mm_setup1_task<DP, BWD>(p, r, task, lane, s_s, sLw[warp], sQw[warp], spw[warp][0], spw[warp][1], spw[warp][2]);
+}
+
 template <int KS> struct RowOpConsts;
 template <int KS>
 __device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, const double* __restrict__ zr,
@@ -269,15 +276,13 @@ __device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, c
 
 // stage 2: the throughput part: one CTA (128 threads) per task sweeps the centres
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
-    const int r = blockIdx.y;
+__device__ __forceinline__ void mm_setup2_task(const MMParams& p, int r, int task) {
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
     const MMWs& L = p.L;
     const int np = L.np;
     constexpr int ldz = DP <= 4 ? 4 : (DP <= 12 ? 12 : 20);   // == L.ldz (ldz_of), compile-time so /,% by it are cheap
     const int tid = threadIdx.x;
-    const int task = BWD ? blockIdx.x + E : blockIdx.x;
 
     __shared__ double sQa[MAXD * MAXD], sQb[MAXD * MAXD];
     __shared__ double sm[MAXD], pa[MAXD], pb[MAXD];
@@ -436,6 +441,28 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
     }
 }
 
+template <int DP, bool BWD>
+__global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
+    PDL_ENTRY();
+    mm_setup2_task<DP, BWD>(p, blockIdx.y, BWD ? blockIdx.x + p.gp.E : blockIdx.x);
+}
+
+// forward mode: both stages of one task in ONE launch -- stage 2 only consumes the stage-1 output of its own task,
+// so warp 0 of the task's CTA runs the serial D x D part, a barrier publishes it (global writes of a CTA are
+// visible to the CTA after __syncthreads), then all four warps sweep the centres.  One launch and one dependent
+// kernel boundary less per moment match (two per rollout step with an RBF policy).
+template <int DP>
+__global__ void __launch_bounds__(128, 4) mm_setup_fused_kernel(MMParams p) {
+    PDL_ENTRY();
+    const int r = blockIdx.y, task = blockIdx.x;
+    __shared__ double f_s[MAXD * SLD], f_L[MAXD * SLD], f_Q[MAXD * SLD], f_p[3][MAXD];
+    setup_stage_s<DP>(p, r, f_s);
+    __syncthreads();
+    if (threadIdx.x < 32) mm_setup1_task<DP, false>(p, r, task, threadIdx.x, f_s, f_L, f_Q, f_p[0], f_p[1], f_p[2]);
+    __syncthreads();
+    mm_setup2_task<DP, false>(p, r, task);
+}
+
 // Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
 // U' = 2 EXP_SC p_b o (Qa zeta_row), and the scalar A'[row] = EXP_SC (log sf2_a - 0.5 sum p_a zeta^2 + z_a'Q z_a
 // - 0.5 log det R).  2*ceil(DP/8)*KS DMMA + 2 KS shuffles per 8 rows.  The pair constants (this lane's B fragments
@@ -528,6 +555,18 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
 template <int DP, bool BWD>
 static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
     const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
+    // forward mode: ONE launch while the batch is small (latency regime: every launch on the serial path of a rollout
+    // step counts); big batches keep the two-stage form (stage 1 is register-hungry: fused, it caps the occupancy of the
+    // throughput stage).  PILCO_SETUP_FUSED=0/1 forces either (tuning switch).
+    if (!BWD) {
+        static int mode = -1;
+        if (mode < 0) { const char* e = getenv("PILCO_SETUP_FUSED"); mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }
+        const bool fused = mode == 2 ? (long long)ntask * p.R <= 160 : mode == 1;
+        if (fused) {
+            launch_hi(mm_setup_fused_kernel<DP>, dim3(ntask, p.R), dim3(128), 0, st, p);
+            return;
+        }
+    }
     launch_hi(mm_setup1_kernel<DP, BWD>, dim3((ntask + SETUP_WARPS - 1) / SETUP_WARPS, p.R), dim3(32 * SETUP_WARPS), 0, st, p);
     launch_hi(mm_setup2_kernel<DP, BWD>, dim3(ntask, p.R), dim3(128), 0, st, p);
 }
@@ -731,6 +770,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
 // rpc = row blocks per CTA (launch_tile chooses it: all of them once the grid still covers the SMs)
 template <int KS, int MINB>
 __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p, int rpc) {
+    PDL_ENTRY();
     int a, b;
     pair_decode(blockIdx.y, a, b);
     if (a != b) mm_tile_body<KS, false, false>(p, rpc);
@@ -772,6 +812,7 @@ __device__ __forceinline__ void mm_finish_device(const MMParams& p, int r) {
 }
 
 static __global__ void __launch_bounds__(128) mm_finish_kernel(MMParams p) {
+    PDL_ENTRY();
     mm_finish_device(p, blockIdx.x);
 }
 

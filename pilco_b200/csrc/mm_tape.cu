@@ -23,11 +23,12 @@ static int launch_tape_tile(const MMParams& p, cudaStream_t st) {
     if (p.L.np > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
     size_t smem = mm_tape_smem_bytes(p.L.np, p.L.ldz);
     const dim3 grid(p.TL.cs, p.L.P, p.R);
-    if (variant == 0) mm_tape_tile_kernel<KS, 256><<<grid, 256, smem, st>>>(p);
-    else if (variant == 1) mm_tape_tile_kernel<KS, 304><<<grid, 256, smem, st>>>(p);
+    const bool hi = pilco_small_grid(grid);
+    if (variant == 0) launch_pri(hi, mm_tape_tile_kernel<KS, 256>, grid, dim3(256), smem, st, p);
+    else if (variant == 1) launch_pri(hi, mm_tape_tile_kernel<KS, 304>, grid, dim3(256), smem, st, p);
     else {
         if (variant == 2 && smem < 80 * 1024) smem = 80 * 1024;    // 2 CTAs per SM
-        mm_tape_tile_kernel<KS, 352><<<grid, 256, smem, st>>>(p);
+        launch_pri(hi, mm_tape_tile_kernel<KS, 352>, grid, dim3(256), smem, st, p);
     }
     return PILCO_OK;
 }
@@ -56,6 +57,7 @@ int mm_tape_tile_launch(const MMParams& p, cudaStream_t st) {
 
 template <int DP>
 __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd bp) {
+    PDL_ENTRY();
     extern __shared__ __align__(16) double tb_dyn[];          // [2][np]: per-centre weights u, v
     const pilco_gp_model& gp = bp.gp;
     const MMTapeL& TL = bp.TL;
@@ -336,6 +338,7 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
 
 // sum the task partials -> gm, gs
 __global__ void __launch_bounds__(128) mm_tape_breduce_kernel(MMTapeBwd bp) {
+    PDL_ENTRY();
     const int r = blockIdx.x;
     mm_tape_reduce_device(bp.part + (size_t)r * mm_tape_bwd_part_doubles(bp.gp.D, bp.gp.E), bp.gp.E + bp.TL.P, bp.gp.D,
                           bp.gm + (size_t)r * bp.gm_rs, bp.gs + (size_t)r * bp.gs_rs, bp.accumulate);

@@ -248,6 +248,7 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
 // the other sub-batches to run BESIDE the tile CTAs), 352 -> 80 registers (3 CTAs/SM fit).  No variant spills.
 template <int KS, int LB>
 __global__ void __launch_bounds__(LB, 2) mm_tape_tile_kernel(MMParams p) {
+    PDL_ENTRY();
     int a, b;
     pair_decode(blockIdx.y, a, b);
     if (a == b && p.gp.mode == 0 && p.gp.iK != nullptr) mm_tape_body<KS, true>(p);

@@ -53,6 +53,7 @@ __device__ __forceinline__ void ro_action_tail(const RoDev& p, int r, const doub
 }
 
 __global__ void __launch_bounds__(128) ro_state_kernel(RoDev p) {
+    PDL_ENTRY();
     __shared__ SmallScratch sc;
     const int r = blockIdx.x, t = p.t, Ds = p.Ds, U = p.U, D = Ds + U;
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(128) ro_state_kernel(RoDev p) {
 }
 
 __global__ void __launch_bounds__(128) ro_policy_kernel(RoDev p) {
+    PDL_ENTRY();
     __shared__ SmallScratch sc;
     const int r = blockIdx.x, t = p.t, Ds = p.Ds;
     mm_finish_device(p.pol, r);

@@ -63,6 +63,7 @@ struct RbDev {
 };
 
 __global__ void __launch_bounds__(128) rb_pre_kernel(RbDev p) {
+    PDL_ENTRY();
     const int r = blockIdx.x, Ds = p.Ds, U = p.U, D = Ds + U;
     const int tid = threadIdx.x, nt = blockDim.x;
     const double* gm = p.gm + (size_t)r * Ds;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(128) rb_pre_kernel(RbDev p) {
 }
 
 __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
+    PDL_ENTRY();
     __shared__ SmallScratch sc;
     __shared__ double gMu[MAXD], gSu[MAXD * MAXD], gVu[MAXD * MAXD], gB[MAXD * MAXD], gCd[MAXD];
     const int r = blockIdx.x, Ds = p.Ds, U = p.U, D = Ds + U, t = p.t;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(128) rbf_factor_bwd_kernel(int bf, int Ds, int
                                                              const double* sf2, long long sf2_bs,
                                                              const double* beta, const double* gy,
                                                              double* gX, double* gY, double* gell) {
+    PDL_ENTRY();
     // one CTA per restart, thread n owns centre n: K[n][m] is evaluated once per (n, m, a)
     const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const double* Xr = X + (size_t)r * bf * Ds;

@@ -94,6 +94,36 @@ def gp_factorize(X, Y, ell, sf2, sn2, need_iK=True, mode=0):
     return gp
 
 
+def gp_append(gp, X, Y):
+    """pilco_gp_append: the factorised (unbatched, exact-GP) model ``gp`` with rows appended to its data and unchanged
+    hyper-parameters.  ``X`` [n1,D], ``Y`` [n1,E] hold the old rows first.  Returns a NEW DeviceGP (n changes, so do the
+    padded leading dimension and every workspace size downstream); the old inverse is consumed by the O(n^2 k)
+    block-inverse update, no Cholesky factorisation of the full matrix is done."""
+    if gp.batched or gp.iK is None or gp.mode != 0:
+        raise ValueError("gp_append needs an unbatched exact-GP model with its inverse")
+    X, Y = dev(X), dev(Y)
+    n0, n1 = gp.n, int(X.shape[0])
+    k = n1 - n0
+    if k < 1:
+        raise ValueError("gp_append: no rows appended")
+    D, E = gp.D, gp.E
+    ldk = pad_n(n1)
+    d = device()
+    beta = torch.empty((E, n1), dtype=F64, device=d)
+    iK = torch.empty((E, ldk, ldk), dtype=F64, device=d)
+    info = torch.zeros(1, dtype=torch.int32, device=d)
+    wsb = lib.pilco_gp_append_workspace_bytes(n0, k, E)
+    ws = torch.empty(wsb // 8, dtype=F64, device=d)
+    check(lib.pilco_gp_append(n0, k, D, E, ptr(X), ptr(Y), ptr(gp.ell), ptr(gp.sf2), ptr(gp.sn2),
+                              ptr(gp.iK), gp.ldk, ptr(iK), ldk, ptr(beta), ptr(info), ptr(ws), wsb, stream_ptr()),
+          "gp_append")
+    new = DeviceGP(X, gp.ell, gp.sf2, beta, iK, ldk, mode=0)
+    new.info = info
+    new.Y, new.sn2 = Y, gp.sn2
+    new.appends = getattr(gp, "appends", 0) + 1
+    return new
+
+
 def gp_refactorize(gp):
     """Re-run pilco_gp_factorize in place after gp.X / gp.Y / gp.ell were overwritten (policy optimisation)."""
     B = gp.X.shape[0] if gp.batched else 1

@@ -182,15 +182,46 @@ class MGPR:
         return engine.gp_factorize(self.X, self.Y, self.lengthscales, self.variance, self.noise,
                                    need_iK=(self.mm_mode == 0), mode=self.mm_mode)
 
+    # incremental set_data: rows appended + hyper-parameters unchanged -> O(n^2 k) update of the
+    # resident inverse instead of a new O(n^3) factorisation.  After MAX_APPENDS consecutive appends (round-off of
+    # the block-inverse recursion) or when more rows arrive than the model holds, it is refactorised from scratch.
+    MAX_APPENDS = 8
+    incremental = True
+
+    def _hyper_key(self):
+        return hash(tuple(np.ascontiguousarray(p).tobytes() for p in (self.lengthscales, self.variance, self.noise)))
+
+    def _try_append(self):
+        """The cached model extended by the appended rows, or None when this is not a pure append."""
+        gp, snap = self._cache_gp, getattr(self, "_cache_snap", None)
+        if not self.incremental or gp is None or snap is None or type(self)._factorize is not MGPR._factorize:
+            return None
+        X, Y = self.X, self.Y
+        X0, Y0, hk = snap
+        n0, n1 = X0.shape[0], X.shape[0]
+        if not (n0 < n1 <= 2 * n0) or X.shape[1] != X0.shape[1] or Y.shape[1] != Y0.shape[1] or hk != self._hyper_key():
+            return None
+        if getattr(gp, "appends", 0) >= self.MAX_APPENDS:
+            return None
+        if not (np.array_equal(X[:n0], X0) and np.array_equal(Y[:n0], Y0)):
+            return None
+        new = engine.gp_append(gp, X, Y)
+        return new if int(new.info.max().item()) == 0 else None
+
     def device_gp(self):
-        """Factorised device model (cached until data or hyper-parameters change)."""
+        """Factorised device model, resident until data or hyper-parameters change; appended rows update it in
+        place of a refactorisation (``_try_append``)."""
         key = self._state_key()
         if key != self._cache_key:
-            gp = self._factorize()
-            bad = int(gp.info.max().item())
-            if bad:
-                raise RuntimeError("Cholesky decomposition was not successful (Gram matrix not positive definite)")
+            gp = self._try_append() if self.mm_mode == 0 else None
+            self.last_update = "append" if gp is not None else "factorize"
+            if gp is None:
+                gp = self._factorize()
+                bad = int(gp.info.max().item())
+                if bad:
+                    raise RuntimeError("Cholesky decomposition was not successful (Gram matrix not positive definite)")
             self._cache_gp, self._cache_key = gp, key
+            self._cache_snap = (self.X.copy(), self.Y.copy(), self._hyper_key())
         return self._cache_gp
 
     def calculate_factorizations(self):

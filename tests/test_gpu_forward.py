@@ -254,3 +254,57 @@ def test_rollout_matches_python_port(kind, R):
         assert scaled_err(tm[r, -1].cpu().numpy(), Mr[0]) < 1e-8
         assert scaled_err(tS[r, -1].cpu().numpy(), Sr) < 1e-7
         assert abs(float(rew[r]) - Rr.item()) < 1e-8 * max(1.0, abs(Rr.item()))
+
+
+def test_gp_append_matches_refactorisation():
+    """Incremental set_data (mgpr.py:38-45 with the rows of a new episode appended,
+    inv_double_pendulum.py:102-103): the O(n^2 k) block-inverse update of the resident model (pilco_gp_append) against
+    a full refactorisation of the grown data set -- factors and moment-match outputs, two appends in a row."""
+    from pilco_b200 import engine
+    n0, D, E = 200, 5, 3
+    X, Y, ell, sf2, sn2 = make_gp_problem(n0 + 70, D, E, seed=11)
+    gp = engine.gp_factorize(X[:n0], Y[:n0], ell, sf2, sn2)
+    m, s = make_input(D, seed=3, scale=0.3)
+    for n1 in (n0 + 40, n0 + 70):                      # 200 -> 240 -> 270 (crosses a multiple of 64: ldk 256 -> 320)
+        gp = engine.gp_append(gp, X[:n1], Y[:n1])
+        ref = engine.gp_factorize(X[:n1], Y[:n1], ell, sf2, sn2)
+        assert int(gp.info.max().item()) == 0 and gp.n == n1 and gp.ldk == engine.pad_n(n1)
+        iK, iKr = gp.iK.cpu().numpy(), ref.iK.cpu().numpy()
+        assert np.all(iK[:, n1:, :] == 0) and np.all(iK[:, :, n1:] == 0)
+        assert scaled_err(iK, iKr) < 1e-9
+        assert scaled_err(gp.beta.cpu().numpy(), ref.beta.cpu().numpy()) < 1e-9
+        out, outr = engine.mm_forward(gp, m, s[None]), engine.mm_forward(ref, m, s[None])
+        for a, b in zip(out[:3], outr[:3]):
+            assert scaled_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-9
+    assert gp.appends == 2
+
+
+def test_mgpr_set_data_appends_incrementally():
+    """The class-level policy: appended rows + unchanged hyper-parameters -> resident model updated ('append');
+    anything else (changed hypers, changed old rows, shrinking) -> full refactorisation; same predictions either way."""
+    from pilco.models import MGPR
+    n0, D, E = 120, 4, 2
+    X, Y, ell, sf2, sn2 = make_gp_problem(n0 + 50, D, E, seed=5)
+    m, s = make_input(D, seed=2, scale=0.3)
+
+    def fixed(mg):
+        for i, mod in enumerate(mg.models):
+            mod.kernel.lengthscales.assign(ell[i]); mod.kernel.variance.assign(sf2[i]); mod.likelihood.variance.assign(sn2[i])
+    mg = MGPR((X[:n0], Y[:n0])); fixed(mg)
+    mg.predict_on_noisy_inputs(m, s)
+    assert mg.last_update == "factorize"
+    mg.set_data((X[:n0 + 30], Y[:n0 + 30]))
+    M1, S1, V1 = mg.predict_on_noisy_inputs(m, s)
+    assert mg.last_update == "append"
+    ref = MGPR((X[:n0 + 30], Y[:n0 + 30])); fixed(ref)
+    Mr, Sr, Vr = ref.predict_on_noisy_inputs(m, s)
+    for a, b in ((M1, Mr), (S1, Sr), (V1, Vr)):
+        assert scaled_err(a, b) < 1e-9
+    mg.models[0].kernel.lengthscales.assign(ell[0] * 1.1)          # hyper-parameters changed -> refactorise
+    mg.set_data((X[:n0 + 50], Y[:n0 + 50]))
+    mg.predict_on_noisy_inputs(m, s)
+    assert mg.last_update == "factorize"
+    X2 = X[:n0 + 50].copy(); X2[0, 0] += 0.5                       # an OLD row changed -> not an append
+    mg.set_data((np.vstack([X2, X[:5] + 0.1]), np.vstack([Y[:n0 + 50], Y[:5]])))
+    mg.predict_on_noisy_inputs(m, s)
+    assert mg.last_update == "factorize"
