@@ -139,6 +139,19 @@ int pilco_gp_nlml(int n, int D, int E, int B,
                   double* nlml, double* g_ell, double* g_sf2, double* g_sn2, int* info,
                   void* ws, size_t ws_bytes, pilco_stream_t stream);
 
+/* FITC training objective (sparse half): value and gradient of the collapsed FITC bound
+ * (gpflow.models.GPRFITC.training_loss as SMGPR.optimize minimises it, pilco/models/smgpr.py:16-22 via
+ * mgpr.py:47-75; no priors) w.r.t. the constrained hyper-parameters AND the inducing inputs, batched over B
+ * parameter sets x E outputs -- every output trains its own Z [Mi,D].  X [N,D], Y [N,E] are shared by the batch;
+ * Z [B,E,Mi,D], ell [B,E,D], sf2/sn2 [B,E].  Outputs nlml [B,E], g_ell [B,E,D], g_sf2, g_sn2 [B,E], g_Z [B,E,Mi,D].
+ * info[b] bit 1: a Cholesky factorisation (Kuu + 1e-6 I, or I + V diag(1/nu) V') failed. */
+size_t pilco_fitc_nlml_workspace_bytes(int N, int Mi, int D, int E, int B);
+int pilco_fitc_nlml(int N, int Mi, int D, int E, int B,
+                    const double* X, const double* Y, const double* Z,
+                    const double* ell, const double* sf2, const double* sn2,
+                    double* nlml, double* g_ell, double* g_sf2, double* g_sn2, double* g_Z, int* info,
+                    void* ws, size_t ws_bytes, pilco_stream_t stream);
+
 /* Replaces SMGPR.calculate_factorizations (pilco/models/smgpr.py:24-45; gp1.m:52-82): FITC over
  * Mi inducing points Z.  Outputs iK[E,ldk,ldk] (zero padded) and beta[E,Mi].
  * ws: scratch of pilco_fitc_workspace_bytes(N, Mi, E) bytes. */

@@ -75,6 +75,8 @@ SIGNATURES = {
                                                             c_dp, C.c_size_t, c_dp]),
     "pilco_gp_nlml_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "pilco_gp_nlml": (C.c_int, [C.c_int] * 4 + [c_dp, c_ll] * 5 + [c_dp] * 5 + [c_dp, C.c_size_t, c_dp]),
+    "pilco_fitc_nlml_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
+    "pilco_fitc_nlml": (C.c_int, [C.c_int] * 5 + [c_dp] * 6 + [c_dp] * 6 + [c_dp, C.c_size_t, c_dp]),
     "pilco_fitc_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "pilco_fitc_factorize": (C.c_int, [C.c_int] * 4 + [c_dp] * 6 + [c_dp, C.c_int, c_dp, c_dp, c_dp,
                                                                   C.c_size_t, c_dp]),

@@ -616,6 +616,249 @@ int pilco_gp_nlml(int n, int D, int E, int B,
     return PILCO_OK;
 }
 
+// ---- FITC training objective on the device (second half) -----------------------------------
+// Replaces gpflow.models.GPRFITC.training_loss + TF autodiff as used by SMGPR.optimize (pilco/models/smgpr.py:16-22 via
+// mgpr.py:47-75): value and gradient w.r.t. (ell, sf2, sn2, Z) of the collapsed FITC bound, batched over
+// B hyper-parameter sets x E outputs (every output trains its own inducing inputs Z).  Stage by stage the algorithm of
+// oracle/fitc_staged.py (checked against torch autograd there):
+//   Kuf, Kuu -> Luu = chol(Kuu + 1e-6 I) -> V = Luu^-1 Kuf -> nu = sf2 + sn2 - colsum(V o V) -> B = I + V diag(1/nu) V'
+//   -> L = chol(B) -> alpha = V (y/nu), gamma = L^-1 alpha -> value;   reverse sweep with two Cholesky adjoints
+//   (Kbar = sym(L^-T Phi(L' Lbar) L^-1)) and the SE-ARD kernel adjoints.  All N-sized products are GEMMs (gemm_kernel).
+struct FitcWs { size_t Kuf, V, T1, T2, Kuu0, Luu, LinvU, Bm, LinvB, Pm, Qm, Ts, nu, ynu, nub, al, ga, ab, part, per_z; };
+static FitcWs fitc_ws_layout(int N, int Mi, int D) {
+    FitcWs W; size_t o = 0;
+    const size_t ldm = pad64(Mi), ldn = pad64(N);
+    auto take = [&](size_t len) { size_t at = o; o += (len + 1) & ~(size_t)1; return at; };
+    W.Kuf = take(ldm * ldn); W.V = take(ldm * ldn); W.T1 = take(ldm * ldn); W.T2 = take(ldm * ldn);
+    W.Kuu0 = take(ldm * ldm); W.Luu = take(ldm * ldm); W.LinvU = take(ldm * ldm); W.Bm = take(ldm * ldm);
+    W.LinvB = take(ldm * ldm); W.Pm = take(ldm * ldm); W.Qm = take(ldm * ldm); W.Ts = take(ldm * ldm);
+    W.nu = take(ldn); W.ynu = take(ldn); W.nub = take(ldn);
+    W.al = take(ldm); W.ga = take(ldm); W.ab = take(ldm);
+    W.part = take((size_t)Mi * (MAXD + 2));
+    W.per_z = o;
+    return W;
+}
+
+// per column n: nu, y/nu and Vs = V / nu
+__global__ void fitc_nu_kernel(int Mi, int N, int E, const double* V, int ldn, long long zs, const double* Y,
+                               const double* sf2, const double* sn2, double* Vs, double* nu, double* ynu) {
+    const int z = blockIdx.y, e = z % E;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const double* Vz = V + (size_t)z * zs + n;
+    double ss = 0.0;
+    for (int i = 0; i < Mi; ++i) { const double v = Vz[(size_t)i * ldn]; ss = fma(v, v, ss); }
+    const double nv = sf2[z] + sn2[z] - ss;
+    nu[(size_t)z * zs + n] = nv;
+    ynu[(size_t)z * zs + n] = Y[(size_t)n * E + e] / nv;
+    double* Vsz = Vs + (size_t)z * zs + n;
+    for (int i = 0; i < Mi; ++i) Vsz[(size_t)i * ldn] = Vz[(size_t)i * ldn] / nv;
+}
+// (the three vectors above live in the per-z workspace: same stride zs as the matrices)
+
+__global__ void add_diag_const_kernel(int n, double* A, int ld, long long ms, double c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)blockIdx.y * ms + (size_t)i * ld + i] += c;
+}
+
+// Pm = tril(Lbar), Lbar = ab gamma' + diag(1 / L_ii)      (Lbar of the value w.r.t. L = chol(B))
+__global__ void fitc_lbar_kernel(int Mi, const double* L, int ld, long long zs, const double* ab, const double* ga, double* Pm) {
+    const int z = blockIdx.z, j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= Mi || j >= Mi) return;
+    double v = 0.0;
+    if (j <= i) {
+        v = ab[(size_t)z * zs + i] * ga[(size_t)z * zs + j];
+        if (i == j) v += 1.0 / L[(size_t)z * zs + (size_t)i * ld + i];
+    }
+    Pm[(size_t)z * zs + (size_t)i * ld + j] = v;
+}
+// mode 0: zero the strict upper triangle;  1: Phi (lower triangle, diagonal halved);  2: symmetrise
+__global__ void tri_op_kernel(int n, double* A, int ld, long long zs, int mode) {
+    const int z = blockIdx.z, j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= n || j >= n) return;
+    double* Az = A + (size_t)z * zs;
+    if (mode == 2) { if (j < i) { const double v = 0.5 * (Az[(size_t)i * ld + j] + Az[(size_t)j * ld + i]); Az[(size_t)i * ld + j] = v; Az[(size_t)j * ld + i] = v; } return; }
+    if (j > i) Az[(size_t)i * ld + j] = 0.0;
+    else if (mode == 1 && i == j) Az[(size_t)i * ld + j] *= 0.5;
+}
+// per column n:  nu_bar and V_bar (in place over BV)
+__global__ void fitc_cols_bwd_kernel(int Mi, int N, int E, const double* V, double* BV, int ldn, long long zs, const double* Y,
+                                     const double* nu, const double* ynu, const double* ab, double* nub) {
+    const int z = blockIdx.y, e = z % E;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const double* Vz = V + (size_t)z * zs + n;
+    double* Bz = BV + (size_t)z * zs + n;
+    const double* abz = ab + (size_t)z * zs;
+    double s1 = 0.0, a = 0.0;
+    for (int i = 0; i < Mi; ++i) { const double v = Vz[(size_t)i * ldn]; s1 = fma(v, Bz[(size_t)i * ldn], s1); a = fma(abz[i], v, a); }
+    const double nv = nu[(size_t)z * zs + n], y = Y[(size_t)n * E + e], in2 = 1.0 / (nv * nv);
+    const double nb = -s1 * in2 + a * y * in2 - 0.5 * y * y * in2 + 0.5 / nv;     // (alpha_bar = -ab)
+    nub[(size_t)z * zs + n] = nb;
+    const double yn = ynu[(size_t)z * zs + n];
+    for (int i = 0; i < Mi; ++i)
+        Bz[(size_t)i * ldn] = 2.0 * Bz[(size_t)i * ldn] / nv - abz[i] * yn - 2.0 * Vz[(size_t)i * ldn] * nb;
+}
+// kernel adjoints, one CTA per (z, inducing point i):  Guf = Kuf_bar o Kuf (row i), Guu = Kuu_bar o Kuu (row i, symmetric)
+//   gZ[i,d] = -( sum_n Guf (z_id - x_nd) + 2 sum_j Guu (z_id - z_jd) ) / ell_d^2
+//   part[i] = [ sum_n Guf dzx_d^2 + sum_j Guu dzz_d^2  (d < D) | sum Guf + sum Guu ]
+__global__ void __launch_bounds__(128) fitc_adjoint_kernel(int Mi, int N, int D, const double* X, const double* Z, const double* ell,
+                                                           const double* Kuf, const double* Kufb, int ldn,
+                                                           const double* Kuu0, const double* Kuub, int ldm, long long zs,
+                                                           double* part, double* gZ) {
+    const int z = blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
+    const double* Zz = Z + (size_t)z * Mi * D;
+    __shared__ double sred[(2 * MAXD + 1) * 4], sout[2 * MAXD + 1];
+    double zi[MAXD], acc[2 * MAXD + 1];
+#pragma unroll
+    for (int d = 0; d < MAXD; ++d) zi[d] = d < D ? Zz[(size_t)i * D + d] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 2 * MAXD + 1; ++k) acc[k] = 0.0;
+    const double* kf = Kuf + (size_t)z * zs + (size_t)i * ldn;
+    const double* kb = Kufb + (size_t)z * zs + (size_t)i * ldn;
+    for (int n = tid; n < N; n += blockDim.x) {
+        const double gq = kf[n] * kb[n];
+        acc[2 * MAXD] += gq;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = zi[d] - X[(size_t)n * D + d]; acc[d] = fma(gq, df, acc[d]); acc[MAXD + d] = fma(gq * df, df, acc[MAXD + d]); }
+    }
+    const double* ku = Kuu0 + (size_t)z * zs + (size_t)i * ldm;
+    const double* kub = Kuub + (size_t)z * zs + (size_t)i * ldm;
+    for (int j = tid; j < Mi; j += blockDim.x) {
+        const double gq = ku[j] * kub[j];
+        acc[2 * MAXD] += gq;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) if (d < D) { const double df = zi[d] - Zz[(size_t)j * D + d]; acc[d] = fma(2.0 * gq, df, acc[d]); acc[MAXD + d] = fma(gq * df, df, acc[MAXD + d]); }
+    }
+    block_sum<2 * MAXD + 1>(acc, 2 * MAXD + 1, sred, sout);
+    if (tid < D) {
+        const double l = ell[(size_t)z * D + tid];
+        gZ[((size_t)z * Mi + i) * D + tid] = -sout[tid] / (l * l);
+        part[(size_t)z * zs + (size_t)i * (MAXD + 2) + tid] = sout[MAXD + tid];
+    }
+    if (tid == 0) part[(size_t)z * zs + (size_t)i * (MAXD + 2) + MAXD] = sout[2 * MAXD];
+}
+// value and the remaining gradients of one (b, e)
+__global__ void __launch_bounds__(256) fitc_final_kernel(int Mi, int N, int D, int E, const double* Y, const double* ell, const double* sf2,
+                                                         const double* L, int ldm, const double* nu, const double* nub, const double* ga,
+                                                         const double* part, long long zs,
+                                                         double* nlml, double* g_ell, double* g_sf2, double* g_sn2) {
+    const int z = blockIdx.x, e = z % E, tid = threadIdx.x;
+    __shared__ double sred[(MAXD + 4) * 8], sout[MAXD + 4];
+    double acc[MAXD + 4];                     // [0..D): ell pieces, [MAXD]: sum G, [MAXD+1]: sum nu_bar, [MAXD+2]: value pieces
+#pragma unroll
+    for (int k = 0; k < MAXD + 4; ++k) acc[k] = 0.0;
+    for (int n = tid; n < N; n += blockDim.x) {
+        const double nv = nu[(size_t)z * zs + n], y = Y[(size_t)n * E + e];
+        acc[MAXD + 1] += nub[(size_t)z * zs + n];
+        acc[MAXD + 2] += 0.5 * y * y / nv + 0.5 * log(nv);
+    }
+    for (int i = tid; i < Mi; i += blockDim.x) {
+        const double g = ga[(size_t)z * zs + i];
+        acc[MAXD + 2] += -0.5 * g * g + log(L[(size_t)z * zs + (size_t)i * ldm + i]);
+        const double* pr = part + (size_t)z * zs + (size_t)i * (MAXD + 2);
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) if (d < D) acc[d] += pr[d];
+        acc[MAXD] += pr[MAXD];
+    }
+    block_sum<MAXD + 4>(acc, MAXD + 4, sred, sout);
+    if (tid < D) { const double l = ell[(size_t)z * D + tid]; g_ell[(size_t)z * D + tid] = sout[tid] / (l * l * l); }
+    if (tid == 0) {
+        nlml[z] = sout[MAXD + 2] + 0.5 * N * 1.8378770664093453;            // log(2 pi)
+        g_sf2[z] = sout[MAXD + 1] + sout[MAXD] / sf2[z];
+        g_sn2[z] = sout[MAXD + 1];
+    }
+}
+
+size_t pilco_fitc_nlml_workspace_bytes(int N, int Mi, int D, int E, int B) {
+    if (N < 1 || Mi < 1 || D < 1 || D > MAXD || E < 1 || B < 1) return 0;
+    return fitc_ws_layout(N, Mi, D).per_z * (size_t)B * E * sizeof(double);
+}
+
+// adjoint of L = chol(K):  out = sym( Linv' Phi(L' tril(Lbar)) Linv );  Lbar in Pm (destroyed), result in Qm
+static int chol_backward(cudaStream_t st, int Zb, int Mi, const double* L, const double* Linv, double* Pm, double* Qm, int ldm, long long zs) {
+    const dim3 g2((Mi + 31) / 32, (Mi + 7) / 8, Zb), b2(32, 8);
+    tri_op_kernel<<<g2, b2, 0, st>>>(Mi, Pm, ldm, zs, 0);                                     // tril(Lbar)
+    int rc = gemm(st, Zb, Mi, Mi, Mi, 1, 0, 1.0, L, ldm, zs, Pm, ldm, zs, 0.0, Qm, ldm, zs);  // L' tril(Lbar)
+    if (rc) return rc;
+    tri_op_kernel<<<g2, b2, 0, st>>>(Mi, Qm, ldm, zs, 1);                                     // Phi
+    rc = gemm(st, Zb, Mi, Mi, Mi, 1, 0, 1.0, Linv, ldm, zs, Qm, ldm, zs, 0.0, Pm, ldm, zs);   // Linv' P
+    if (rc) return rc;
+    rc = gemm(st, Zb, Mi, Mi, Mi, 0, 0, 1.0, Pm, ldm, zs, Linv, ldm, zs, 0.0, Qm, ldm, zs);   // ... Linv
+    if (rc) return rc;
+    tri_op_kernel<<<g2, b2, 0, st>>>(Mi, Qm, ldm, zs, 2);                                     // sym
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+int pilco_fitc_nlml(int N, int Mi, int D, int E, int B,
+                    const double* X, const double* Y,                 /* [N,D], [N,E] shared by the batch */
+                    const double* Z,                                  /* [B,E,Mi,D] */
+                    const double* ell, const double* sf2, const double* sn2,   /* [B,E,D], [B,E], [B,E] */
+                    double* nlml, double* g_ell, double* g_sf2, double* g_sn2, double* g_Z, int* info,
+                    void* ws, size_t ws_bytes, pilco_stream_t stream) {
+    if (!X || !Y || !Z || !ell || !sf2 || !sn2 || !nlml || !g_ell || !g_sf2 || !g_sn2 || !g_Z || !ws) return PILCO_ERR_NULL;
+    if (N < 1 || Mi < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || B < 1) return PILCO_ERR_DIM;
+    if (ws_bytes < pilco_fitc_nlml_workspace_bytes(N, Mi, D, E, B)) return PILCO_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Zb = B * E, ldm = pad64(Mi), ldn = pad64(N);
+    const FitcWs W = fitc_ws_layout(N, Mi, D);
+    const long long zs = (long long)W.per_z;                           // every array is addressed base + z*zs
+    double* w = (double*)ws;
+    if (info) cudaMemsetAsync(info, 0, sizeof(int) * B, st);
+    cudaMemsetAsync(ws, 0, W.per_z * (size_t)Zb * sizeof(double), st);
+    // Gram blocks; per (b,e) inducing inputs: the batch index of gram_kernel runs over z with E' = 1
+    GramArgs guu{Mi, Mi, D, 1, Z, (long long)Mi * D, Z, (long long)Mi * D, ell, D, sf2, 1, nullptr, 0, 0.0, w + W.Kuu0, ldm, zs, Mi, Mi, 0};
+    launch_hi(gram_kernel, dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st, guu);
+    GramArgs gul{Mi, Mi, D, 1, Z, (long long)Mi * D, Z, (long long)Mi * D, ell, D, sf2, 1, nullptr, 0, 1e-6, w + W.Luu, ldm, zs, Mi, Mi, 0};
+    launch_hi(gram_kernel, dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st, gul);
+    GramArgs guf{Mi, N, D, 1, Z, (long long)Mi * D, X, 0, ell, D, sf2, 1, nullptr, 0, 0.0, w + W.Kuf, ldn, zs, Mi, N, 0};
+    launch_hi(gram_kernel, dim3((N + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st, guf);
+    CUDA_LAUNCH_CHECK();
+    launch_hi(chol_kernel, dim3(Zb), dim3(256), 0, st, Mi, w + W.Luu, ldm, zs, E, info);
+    tri_op_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st>>>(Mi, w + W.Luu, ldm, zs, 0);     // strict upper := 0
+    CUDA_LAUNCH_CHECK();
+    int rc = tri_inverse(st, Zb, Mi, w + W.Luu, ldm, zs, w + W.LinvU, ldm, zs, w + W.Ts, zs);
+    if (rc) return rc;
+    rc = gemm(st, Zb, Mi, N, Mi, 0, 0, 1.0, w + W.LinvU, ldm, zs, w + W.Kuf, ldn, zs, 0.0, w + W.V, ldn, zs);        // V
+    if (rc) return rc;
+    fitc_nu_kernel<<<dim3((N + 127) / 128, Zb), 128, 0, st>>>(Mi, N, E, w + W.V, ldn, zs, Y, sf2, sn2, w + W.T1, w + W.nu, w + W.ynu);
+    CUDA_LAUNCH_CHECK();
+    rc = gemm(st, Zb, Mi, Mi, N, 0, 1, 1.0, w + W.T1, ldn, zs, w + W.V, ldn, zs, 0.0, w + W.Bm, ldm, zs);            // V diag(1/nu) V'
+    if (rc) return rc;
+    add_diag_const_kernel<<<dim3((Mi + 127) / 128, Zb), 128, 0, st>>>(Mi, w + W.Bm, ldm, zs, 1.0);
+    launch_hi(chol_kernel, dim3(Zb), dim3(256), 0, st, Mi, w + W.Bm, ldm, zs, E, info);                          // L (in Bm)
+    tri_op_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st>>>(Mi, w + W.Bm, ldm, zs, 0);
+    CUDA_LAUNCH_CHECK();
+    rc = tri_inverse(st, Zb, Mi, w + W.Bm, ldm, zs, w + W.LinvB, ldm, zs, w + W.Ts, zs);
+    if (rc) return rc;
+    matvec_kernel<<<dim3(Mi, Zb), 32, 0, st>>>(Mi, N, 0, w + W.V, ldn, zs, w + W.ynu, zs, 1, w + W.al, zs);          // alpha
+    matvec_kernel<<<dim3(Mi, Zb), 32, 0, st>>>(Mi, Mi, 0, w + W.LinvB, ldm, zs, w + W.al, zs, 1, w + W.ga, zs);      // gamma
+    matvec_kernel<<<dim3(Mi, Zb), 32, 0, st>>>(Mi, Mi, 1, w + W.LinvB, ldm, zs, w + W.ga, zs, 1, w + W.ab, zs);      // ab = -alpha_bar
+    CUDA_LAUNCH_CHECK();
+    // Bbar = chol_backward(L, Lbar)
+    fitc_lbar_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st>>>(Mi, w + W.Bm, ldm, zs, w + W.ab, w + W.ga, w + W.Pm);
+    rc = chol_backward(st, Zb, Mi, w + W.Bm, w + W.LinvB, w + W.Pm, w + W.Qm, ldm, zs);
+    if (rc) return rc;
+    rc = gemm(st, Zb, Mi, N, Mi, 0, 0, 1.0, w + W.Qm, ldm, zs, w + W.V, ldn, zs, 0.0, w + W.T1, ldn, zs);           // BV = Bbar V
+    if (rc) return rc;
+    fitc_cols_bwd_kernel<<<dim3((N + 127) / 128, Zb), 128, 0, st>>>(Mi, N, E, w + W.V, w + W.T1, ldn, zs, Y, w + W.nu, w + W.ynu, w + W.ab, w + W.nub);
+    CUDA_LAUNCH_CHECK();
+    rc = gemm(st, Zb, Mi, N, Mi, 1, 0, 1.0, w + W.LinvU, ldm, zs, w + W.T1, ldn, zs, 0.0, w + W.T2, ldn, zs);        // Kuf_bar = Luu^-T Vbar
+    if (rc) return rc;
+    rc = gemm(st, Zb, Mi, Mi, N, 0, 1, -1.0, w + W.T2, ldn, zs, w + W.V, ldn, zs, 0.0, w + W.Pm, ldm, zs);           // Luu_bar = -Kuf_bar V'
+    if (rc) return rc;
+    rc = chol_backward(st, Zb, Mi, w + W.Luu, w + W.LinvU, w + W.Pm, w + W.Qm, ldm, zs);                           // Kuu_bar
+    if (rc) return rc;
+    fitc_adjoint_kernel<<<dim3(Mi, Zb), 128, 0, st>>>(Mi, N, D, X, Z, ell, w + W.Kuf, w + W.T2, ldn, w + W.Kuu0, w + W.Qm, ldm, zs,
+                                                      w + W.part, g_Z);
+    CUDA_LAUNCH_CHECK();
+    fitc_final_kernel<<<Zb, 256, 0, st>>>(Mi, N, D, E, Y, ell, sf2, w + W.Bm, ldm, w + W.nu, w + W.nub, w + W.ga, w + W.part, zs,
+                                          nlml, g_ell, g_sf2, g_sn2);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
 size_t pilco_fitc_workspace_bytes(int N, int Mi, int E) {
     if (N < 1 || Mi < 1 || E < 1) return 0;
     const size_t ldm = pad64(Mi) + 64, ldn = pad64(N);

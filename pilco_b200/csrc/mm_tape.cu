@@ -56,7 +56,7 @@ int mm_tape_tile_launch(const MMParams& p, cudaStream_t st) {
 #define TB_WARPS 4
 
 template <int DP>
-__global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd bp) {
+__global__ void __launch_bounds__(TB_THREADS, 6) mm_tape_bfinish_kernel(MMTapeBwd bp) {
     PDL_ENTRY();
     extern __shared__ __align__(16) double tb_dyn[];          // [2][np]: per-centre weights u, v
     const pilco_gp_model& gp = bp.gp;
@@ -93,6 +93,8 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
     const bool is_out = task < E;
     int a = task, b = task, q = 0;
     const double* HZg = nullptr;
+    const double* hrg = nullptr;
+    const double* hcg = nullptr;
     if (is_out) {
         // ---- output task: W_a = (s + Lambda_a^2)^-1, c_a, per-centre weights u_n = gw_n w_n, v_n = w_n ----
         if (tid < DP) {
@@ -166,16 +168,8 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
             sW[i * SLD + j] = in ? Qg[i * D + j] : 0.0;
             sCm[i * SLD + j] = in ? Cg[i * D + j] : 0.0;
         }
-        const double* hr = tpr + TL.hr + (size_t)q * np;
-        const double* hc = tpr + TL.hc + (size_t)q * TL.cs * np;
-        for (int nn = tid; nn < np; nn += blockDim.x) {
-            double u = 0.0, v = 0.0;
-            if (nn < n) {
-                u = hr[nn];
-                for (int k = 0; k < TL.cs; ++k) v += hc[(size_t)k * np + nn];
-            }
-            su[nn] = u; sv[nn] = v;
-        }
+        hrg = tpr + TL.hr + (size_t)q * np;                     // weights u = hr, v = sum of the row splits of hc:
+        hcg = tpr + TL.hc + (size_t)q * TL.cs * np;             // read straight from the tape inside the k-loop
         HZg = tpr + TL.HZ + (size_t)q * np * TL.ldh;
     }
     __syncthreads();
@@ -188,7 +182,7 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
     for (int i = 0; i < TX * TX; ++i) { ch[i][0] = ch[i][1] = 0.0; }
     // TBU k-steps per trip: all their operands are loaded first (the tape was written a whole rollout ago and comes
     // from DRAM -- the loads of a trip are independent, so their latencies overlap), then the DMMAs run
-    constexpr int TBU = (TX <= 2) ? 4 : 2;
+    constexpr int TBU = 2;
     const int nks = (n + 3) >> 2;
     for (int ks0 = warp; ks0 < nks; ks0 += TB_WARPS * TBU) {
         double zx[TBU][TX], bh[TBU][TX], uu[TBU], vv[TBU];
@@ -196,7 +190,12 @@ __global__ void __launch_bounds__(TB_THREADS) mm_tape_bfinish_kernel(MMTapeBwd b
         for (int k = 0; k < TBU; ++k) {
             const int row = 4 * (ks0 + k * TB_WARPS) + t;
             const bool live = row < n;                            // (also false for k-steps beyond nks)
-            uu[k] = live ? su[row] : 0.0; vv[k] = live ? sv[row] : 0.0;
+            double uk = 0.0, vk = 0.0;
+            if (live) {
+                if (is_out) { uk = su[row]; vk = sv[row]; }
+                else { uk = hrg[row]; for (int c2 = 0; c2 < TL.cs; ++c2) vk += hcg[(size_t)c2 * np + row]; }
+            }
+            uu[k] = uk; vv[k] = vk;
 #pragma unroll
             for (int tl = 0; tl < TX; ++tl) {
                 const int c = g + 8 * tl;

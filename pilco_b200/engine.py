@@ -167,6 +167,35 @@ class GpNlml:
                 self.info.cpu().numpy() != 0)
 
 
+class FitcNlml:
+    """pilco_fitc_nlml with persistent buffers: FITC bound and its gradient w.r.t. (ell, sf2, sn2, Z) for B
+    hyper-parameter sets x E outputs (each output with its own inducing inputs)."""
+
+    def __init__(self, X, Y, Mi, B):
+        d = device()
+        self.X, self.Y = dev(X), dev(Y)
+        self.N, self.D = self.X.shape
+        self.E, self.B, self.Mi = self.Y.shape[1], int(B), int(Mi)
+        B, E, D, Mi = self.B, self.E, self.D, self.Mi
+        mk = lambda *shape: torch.empty(shape, dtype=F64, device=d)
+        self.Z, self.ell, self.sf2, self.sn2 = mk(B, E, Mi, D), mk(B, E, D), mk(B, E), mk(B, E)
+        self.nlml, self.g_ell, self.g_sf2, self.g_sn2, self.g_Z = mk(B, E), mk(B, E, D), mk(B, E), mk(B, E), mk(B, E, Mi, D)
+        self.info = torch.zeros(B, dtype=torch.int32, device=d)
+        self.wsb = lib.pilco_fitc_nlml_workspace_bytes(self.N, Mi, D, E, B)
+        self.ws = torch.empty(self.wsb // 8, dtype=F64, device=d)
+
+    def __call__(self, Z, ell, sf2, sn2):
+        """numpy [B,E,Mi,D], [B,E,D], [B,E], [B,E] -> nlml, g_ell, g_sf2, g_sn2, g_Z, bad [B] (numpy)"""
+        for dst, src in ((self.Z, Z), (self.ell, ell), (self.sf2, sf2), (self.sn2, sn2)):
+            dst.copy_(torch.as_tensor(np.ascontiguousarray(src)))
+        check(lib.pilco_fitc_nlml(self.N, self.Mi, self.D, self.E, self.B, ptr(self.X), ptr(self.Y), ptr(self.Z),
+                                  ptr(self.ell), ptr(self.sf2), ptr(self.sn2), ptr(self.nlml), ptr(self.g_ell),
+                                  ptr(self.g_sf2), ptr(self.g_sn2), ptr(self.g_Z), ptr(self.info), ptr(self.ws), self.wsb,
+                                  stream_ptr()), "fitc_nlml")
+        return (self.nlml.cpu().numpy(), self.g_ell.cpu().numpy(), self.g_sf2.cpu().numpy(), self.g_sn2.cpu().numpy(),
+                self.g_Z.cpu().numpy(), self.info.cpu().numpy() != 0)
+
+
 def fitc_factorize(X, Z, Y, ell, sf2, sn2):
     """pilco_fitc_factorize: FITC over inducing points Z -> DeviceGP centred on Z."""
     X, Z, Y, ell, sf2, sn2 = dev(X), dev(Z), dev(Y), dev(ell), dev(sf2), dev(sn2)

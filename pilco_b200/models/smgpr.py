@@ -45,8 +45,12 @@ class SMGPR(MGPR):
             self.models.append(GPRFITCModel((data[0], data[1][:, i:i + 1]), kern, Z))
 
     def optimize(self, restarts=1, maxiter=None):
-        """FITC objective with trainable inducing inputs: host logic (gp_training.fitc_loss), see DESIGN.md section 9."""
-        return self.optimize_host(restarts=restarts, maxiter=maxiter)
+        """FITC objective with trainable inducing inputs, on the device: all outputs and restarts in lock step, value
+        and analytic gradient from ``pilco_fitc_nlml`` (gp_device_training.optimize_smgpr).  ``optimize_host`` keeps
+        the torch-CPU autograd path as the cross-check the tests use."""
+        from .. import gp_device_training
+        self.optimizers = [True] * len(self.models)
+        return gp_device_training.optimize_smgpr(self, restarts=restarts, maxiter=maxiter)
 
     @property
     def Z(self):
