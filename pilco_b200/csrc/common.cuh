@@ -249,6 +249,26 @@ template <typename... KArgs, typename... Args>
 static inline void launch_hi(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     launch_pri(true, kern, grid, block, smem, st, std::forward<Args>(args)...);
 }
+// "Last CTA" pattern: fold a small per-group follow-up kernel into the kernel that produces its inputs.  Returns true
+// (to every thread) in exactly one CTA of the `count` CTAs sharing `counter`: the last one to arrive, which then sees
+// every global write the others made before arriving.  The winner resets the counter (self-cleaning; the counter
+// array must be zero before the first use).  Results stay deterministic as long as the follow-up work does not
+// depend on WHICH CTA runs it.
+__device__ __forceinline__ bool last_cta_arrives(unsigned* counter, unsigned count) {
+    __shared__ int s_last_flag;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(counter, 1u);
+        s_last_flag = (prev + 1 == count);
+        if (s_last_flag) *counter = 0;
+    }
+    __syncthreads();
+    const bool last = s_last_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
 // tile-type kernels: "glue" (high priority) while the whole grid fits the machine once, bulk work otherwise
 static inline bool pilco_small_grid(dim3 g) { return (long long)g.x * g.y * g.z < 296; }
 #endif       // (kept for the launchers: nothing to upload)

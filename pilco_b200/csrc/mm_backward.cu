@@ -159,14 +159,12 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
 #define BF_CHUNK 128
 
 template <int DP>
-__global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
-    PDL_ENTRY();
+__device__ __forceinline__ void mm_bfinish_task(const MMBwdParams& bp, int r, int task) {
     const MMParams& p = bp.f;
     const pilco_gp_model& gp = p.gp;
     const MMBws& B = bp.B;
     const MMWs& L = B.F;
     const int n = gp.n, D = gp.D, E = gp.E, np = L.np, ldz = L.ldz;
-    const int r = blockIdx.y, task = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     __shared__ double sW[MAXD * SLD];         // W_a (output task) or Q_ab (pair task)
@@ -423,13 +421,13 @@ __global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
 // -------------------------------------------------------------------------------------------------
 // reduce: sum task partials
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) mm_breduce_kernel(MMBwdParams bp) {
-    PDL_ENTRY();
+// sum of the task partials of restart r (all threads of one CTA)
+__device__ __forceinline__ void mm_breduce_body(const MMBwdParams& bp, int r) {
     const MMParams& p = bp.f;
     const pilco_gp_model& gp = p.gp;
     const MMBws& B = bp.B;
     const int n = gp.n, D = gp.D, E = gp.E, np = B.F.np;
-    const int r = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     const double* wsr = p.ws + (size_t)r * B.per_r;
     const double* ell = gp.ell + (size_t)r * gp.ell_bs;
     double* gm = bp.gm + (size_t)r * bp.gm_rs;
@@ -473,6 +471,17 @@ __global__ void __launch_bounds__(128) mm_breduce_kernel(MMBwdParams bp) {
         const double v = -2.0 * gp_ / (l * l * l) + 2.0 * l * wsr[B.Tpa + (size_t)a * MAXD + d];
         gell[e] = bp.accumulate ? gell[e] + v : v;
     }
+}
+
+// finish + reduce in ONE launch: one CTA per task; the last CTA of a restart to arrive sums the task partials (fixed
+// task order: deterministic whichever CTA that is) -- one dependent kernel less on the serial path of the reverse sweep
+template <int DP>
+__global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
+    PDL_ENTRY();
+    const int r = blockIdx.y;
+    mm_bfinish_task<DP>(bp, r, blockIdx.x);
+    unsigned* cnt = reinterpret_cast<unsigned*>(bp.f.ws + (size_t)r * bp.B.per_r + bp.B.cnt);
+    if (last_cta_arrives(cnt, gridDim.x)) mm_breduce_body(bp, r);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -528,8 +537,6 @@ int mm_backward_launch(MMBwdParams bp, cudaStream_t st) {
         default: launch_hi(mm_bfinish_kernel<16>, dim3(gf), dim3(128), 0, st, bp); break;
     }
     CUDA_LAUNCH_CHECK();
-    launch_hi(mm_breduce_kernel, dim3(R), dim3(128), 0, st, bp);
-    CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }
 
@@ -569,6 +576,7 @@ int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const do
     if (((uintptr_t)ws) & 15) return PILCO_ERR_ALIGN;
     MMBwdParams bp = mm_bwd_params(gp, R, m, gp->D, s, (long long)gp->D * gp->D, M, gM, gS, gV,
                                    gm, gp->D, gs, (long long)gp->D * gp->D, gX, gbeta, gell, 0, (double*)ws);
+    mm_bwd_zero_counters(bp.B, (double*)ws, R, (cudaStream_t)stream);
     return mm_backward_launch(bp, (cudaStream_t)stream);
 }
 

@@ -4,7 +4,7 @@
 
 struct MMBws {                      // extra workspace arrays (offsets in doubles, per restart)
     MMWs F;                         // forward-style arrays for ORDERED pairs
-    size_t oQ, oC, oLd, rowout, Tm, Ts, Tpa, Tpb, Tsc, Tz, Tb, per_r;
+    size_t oQ, oC, oLd, rowout, Tm, Ts, Tpa, Tpb, Tsc, Tz, Tb, cnt, per_r;
     int ldr, ntask, P2;
 };
 
@@ -26,6 +26,7 @@ static inline __host__ __device__ MMBws mm_bws_layout(int n, int D, int E, int n
     B.Tsc = take((size_t)B.ntask * 2);
     B.Tz = need_param ? take((size_t)B.ntask * B.F.np * MAXD) : o;
     B.Tb = need_param ? take((size_t)B.ntask * B.F.np) : o;
+    B.cnt = take(2);                // arrival counter of the finish tasks (last_cta_arrives); zero before first use
     B.per_r = o;
     return B;
 }
@@ -46,3 +47,7 @@ MMBwdParams mm_bwd_params(const pilco_gp_model* gp, int R, const double* m, long
                           double* gm, long long gm_rs, double* gs, long long gs_rs,
                           double* gX, double* gbeta, double* gell, int accumulate, double* ws);
 int mm_backward_launch(MMBwdParams bp, cudaStream_t st);
+// zero the arrival counters of a backward workspace (once before the first mm_backward_launch on it)
+static inline void mm_bwd_zero_counters(const MMBws& B, double* ws, int R, cudaStream_t st) {
+    cudaMemset2DAsync(ws + B.cnt, B.per_r * sizeof(double), 0, 2 * sizeof(double), (size_t)R, st);
+}

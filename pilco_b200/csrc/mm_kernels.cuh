@@ -447,20 +447,20 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
     mm_setup2_task<DP, BWD>(p, blockIdx.y, BWD ? blockIdx.x + p.gp.E : blockIdx.x);
 }
 
-// forward mode: both stages of one task in ONE launch -- stage 2 only consumes the stage-1 output of its own task,
+// both stages of one task in ONE launch -- stage 2 only consumes the stage-1 output of its own task,
 // so warp 0 of the task's CTA runs the serial D x D part, a barrier publishes it (global writes of a CTA are
 // visible to the CTA after __syncthreads), then all four warps sweep the centres.  One launch and one dependent
 // kernel boundary less per moment match (two per rollout step with an RBF policy).
-template <int DP>
+template <int DP, bool BWD>
 __global__ void __launch_bounds__(128, 4) mm_setup_fused_kernel(MMParams p) {
     PDL_ENTRY();
-    const int r = blockIdx.y, task = blockIdx.x;
+    const int r = blockIdx.y, task = BWD ? blockIdx.x + p.gp.E : blockIdx.x;     // BWD: ordered pair tasks only
     __shared__ double f_s[MAXD * SLD], f_L[MAXD * SLD], f_Q[MAXD * SLD], f_p[3][MAXD];
     setup_stage_s<DP>(p, r, f_s);
     __syncthreads();
-    if (threadIdx.x < 32) mm_setup1_task<DP, false>(p, r, task, threadIdx.x, f_s, f_L, f_Q, f_p[0], f_p[1], f_p[2]);
+    if (threadIdx.x < 32) mm_setup1_task<DP, BWD>(p, r, task, threadIdx.x, f_s, f_L, f_Q, f_p[0], f_p[1], f_p[2]);
     __syncthreads();
-    mm_setup2_task<DP, false>(p, r, task);
+    mm_setup2_task<DP, BWD>(p, r, task);
 }
 
 // Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
@@ -555,15 +555,15 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
 template <int DP, bool BWD>
 static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
     const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
-    // forward mode: ONE launch while the batch is small (latency regime: every launch on the serial path of a rollout
+    // ONE launch while the batch is small (latency regime: every launch on the serial path of a rollout
     // step counts); big batches keep the two-stage form (stage 1 is register-hungry: fused, it caps the occupancy of the
     // throughput stage).  PILCO_SETUP_FUSED=0/1 forces either (tuning switch).
-    if (!BWD) {
+    {
         static int mode = -1;
         if (mode < 0) { const char* e = getenv("PILCO_SETUP_FUSED"); mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }
         const bool fused = mode == 2 ? (long long)ntask * p.R <= 160 : mode == 1;
         if (fused) {
-            launch_hi(mm_setup_fused_kernel<DP>, dim3(ntask, p.R), dim3(128), 0, st, p);
+            launch_hi(mm_setup_fused_kernel<DP, BWD>, dim3(ntask, p.R), dim3(128), 0, st, p);
             return;
         }
     }

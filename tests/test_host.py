@@ -144,7 +144,7 @@ def test_smgpr_and_controller_host_surface():
     X = np.random.rand(30, 3); Y = np.random.rand(30, 2)
     s = SMGPR((X, Y), num_induced_points=7)
     assert s.Z.numpy().shape == (7, 3) and s.centres.shape == (7, 3)
-    s.optimize(restarts=0, maxiter=5)                                  # FITC training stays on the host
+    s.optimize_host(restarts=0, maxiter=5)                             # host cross-check path (SMGPR.optimize itself runs on the device)
     assert np.all(s.lengthscales > 0)
     rbf = RbfController(3, 2, 11, max_action=2.0)
     assert rbf.models[1].X is rbf.models[0].X                          # shared centres (controllers.py:103-106)

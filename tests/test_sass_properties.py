@@ -49,3 +49,34 @@ def test_tile_kernels_use_dmma_tma_and_no_local_memory():
     metric = [t for n, t in fwd.items() if "ILi3ELi3E" in n][0]                # D = 12 instantiation (metric shape)
     assert metric.count("DMMA.8x8x4") >= 36                                    # 12 per 4-tile group x 3 pair kinds
     assert "MUFU.EX2" not in metric                                            # table exp, not the SFU path
+
+
+def test_taped_path_kernels_use_dmma_and_stay_in_registers():
+    """Round 2: the taped forward tile kernel (what optimize_policy runs) and the tape-driven reverse-sweep kernel.
+    Tile: DMMA for both products (exponent + H.[Z,1]), TMA-staged columns, no local memory at any register variant,
+    table exp.  Finish: the weighted moment sums are DMMA (no DFMA inner product loops), metric-shape instantiation
+    spill-free apart from a few bytes."""
+    tile = _sass(r"mm_tape_tile_kernelILi\d")
+    assert len(tile) == 12                                                     # KS = 1..4 x 3 register variants
+    for name, text in tile.items():
+        assert "DMMA.8x8x4" in text and "UBLKCP" in text and "TRYWAIT" in text, name
+        if "ELi352E" not in name or "ILi4E" not in name:                       # (the 80-register variant of D = 16 spills)
+            assert not re.search(r"\b(STL|LDL)\b", text), "local memory traffic in %s" % name
+        assert "MUFU.EX2" not in text, name
+    metric = [t for n, t in tile.items() if "ILi3ELi256E" in n][0]             # D = 12, default register variant
+    # per octet and 8-column tile: 3 (exponent) + 4 (H.[Z,1]) DMMA; two octets per pass, x 2 pair kinds x {1, 2 live octets}
+    assert metric.count("DMMA.8x8x4") >= 2 * (7 + 14)
+    fin = _sass(r"rb_dyn_finish_kernelILi12E|mm_tape_bfinish_kernelILi12E")
+    assert len(fin) == 2
+    for name, text in fin.items():
+        assert text.count("DMMA.8x8x4") >= 10, name                            # 3 + 3 symmetric tiles + 4 (Z'HZ) per k-step
+        assert len(re.findall(r"\bSTL\b", text)) <= 24, name                   # (a handful of spilled scalars, no arrays)
+
+
+def test_reverse_sweep_policy_kernels_present():
+    """The recomputing VJP kernels that remain on the path (RBF policy, need_param) exist in every instantiation,
+    finish + reduce are one kernel (no mm_breduce_kernel launch any more)."""
+    names = _sass(r"mm_bfinish_kernel|mm_breduce_kernel|mm_setup_fused_kernel")
+    assert sum("mm_bfinish_kernel" in n for n in names) == 4
+    assert not any("mm_breduce_kernel" in n for n in names)
+    assert sum("mm_setup_fused_kernel" in n for n in names) == 8               # DP = 4..16 x {forward, ordered-pair backward}
