@@ -543,10 +543,11 @@ def run_ours(args, cfg):
     # taped forward (pilco_rollout.tape) + tape-driven reverse sweep; device resident and end to end
     # (host parameters in, [reward | gradient] out), one captured graph each
     split3 = split4 = None
+    nsplit_b = max(1, min(args.nsplit_bwd, R))
     if args.with_backward:
-        split3 = engine.SplitRollout(lambda lo, hi: make_plan(lo, hi, grad=True), R, nsplit=nsplit, backward=True)
+        split3 = engine.SplitRollout(lambda lo, hi: make_plan(lo, hi, grad=True), R, nsplit=nsplit_b, backward=True)
         pg4, plans4 = {}, {}
-        split4 = engine.SplitRollout(plan_factory(pg4, plans4, True), R, nsplit=nsplit, backward=True)
+        split4 = engine.SplitRollout(plan_factory(pg4, plans4, True), R, nsplit=nsplit_b, backward=True)
         gkeys = ("W", "b") if bf == 0 else ("X", "Y", "ell")
         first = plans4[next(iter(plans4))]
         gsz = sum(int(np.prod(first.gbuf[k].shape[1:])) for k in gkeys)
@@ -711,7 +712,7 @@ def run_ours(args, cfg):
     fb = None
     if ms_fb is not None:
         fb = {"value": total_steps / (ms_fb * 1e-3), "unit": UNIT, "ms_per_step": ms_fb,
-              "what": "taped forward cascade + tape-driven reverse sweep (policy gradient), device resident",
+              "what": "taped forward cascade + tape-driven reverse sweep (policy gradient), device resident, %d sub-batches on parallel streams" % nsplit_b,
               "e2e": {"value": total_steps / (ms_fb_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_fb_e2e,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_grad.numel()) * 8,
                       "what": "pinned host policy parameters -> device, policy factorisation, taped forward, reverse sweep, [reward | gradient] -> host"}}
@@ -764,7 +765,8 @@ def main():
     ap.add_argument("--no-backward", dest="with_backward", action="store_false", help="skip the forward+backward lines")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false", help="tuning runs: skip the CPU legs")
     ap.add_argument("--no-api-line", dest="api_line", action="store_false", help="skip the PILCO.predict class-API line")
-    ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph")
+    ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph (forward arms)")
+    ap.add_argument("--nsplit-bwd", type=int, default=4, help="... for the forward+backward arms (measured: 4 beats 8 for the reverse sweep)")
     ap.add_argument("--through-api", action="store_true", help="drive PILCO.optimize_policy itself (lock-step L-BFGS-B, sharded restarts)")
     ap.add_argument("--maxiter", type=int, default=10, help="--through-api: L-BFGS-B iterations")
     args = ap.parse_args()

@@ -82,7 +82,7 @@ int pilco_mm_backward(const pilco_gp_model* gp, int R, const double* m, const do
  * pilco_mm_backward_taped turns the tape and the cotangents into gm, gs WITHOUT recomputing an exponential.
  * Only the cotangents of the input moments are produced (the dynamics GP of the policy objective, whose inputs
  * and hyper-parameters are constants, pilco/models/pilco.py:80-82); trainable centres need pilco_mm_backward. */
-size_t pilco_mm_tape_bytes(int n, int D, int E, int R);          /* 0 if n > 2048 */
+size_t pilco_mm_tape_bytes(int n, int D, int E, int R);          /* 0: shape not supported (n > 1024 for D <= 12, n > 704 beyond) */
 size_t pilco_mm_tape_bwd_workspace_bytes(int D, int E, int R);
 int pilco_mm_forward_taped(const pilco_gp_model* gp, int R, const double* m, const double* s,
                            double* M, double* S, double* V, int* info,
@@ -257,7 +257,7 @@ typedef struct pilco_rollout {
 } pilco_rollout;
 
 size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro);
-size_t pilco_rollout_tape_bytes(const pilco_rollout* ro);   /* 0: shape not supported by the taped pass (n > 2048) */
+size_t pilco_rollout_tape_bytes(const pilco_rollout* ro);   /* 0: shape not supported by the taped pass (n > 1024 centres for D <= 12, > 704 beyond) */
 int    pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream);
 
 /* Reverse sweep: gradient of ro->reward[r] (= sum_t E[r(x_t)], the negative of PILCO.training_loss,

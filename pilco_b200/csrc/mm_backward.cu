@@ -235,6 +235,7 @@ __device__ __forceinline__ void mm_bfinish_task(const MMBwdParams& bp, int r, in
         for (int i = 0; i <= 2 * DP; ++i) acc[i] = 0.0;
         for (int c0 = 0; c0 < np; c0 += BF_CHUNK) {
             const int nn = c0 + tid;
+            const int krows = (n - c0) < BF_CHUNK ? (n - c0 > 0 ? n - c0 : 0) : BF_CHUNK;   // staged rows beyond n are zero
             double z[DP], gww = 0.0;
 #pragma unroll
             for (int d = 0; d < DP; ++d) z[d] = 0.0;
@@ -272,7 +273,7 @@ __device__ __forceinline__ void mm_bfinish_task(const MMBwdParams& bp, int r, in
             for (int e = tid; e < DP * DP; e += blockDim.x) {       // sum_n (gw w zeta)[i] zeta[j]
                 const int i = e / DP, j = e % DP;
                 double v = sOm[e];
-                for (int k = 0; k < BF_CHUNK; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
+                for (int k = 0; k < krows; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
                 sOm[e] = v;
             }
             __syncthreads();
@@ -328,6 +329,7 @@ __device__ __forceinline__ void mm_bfinish_task(const MMBwdParams& bp, int r, in
     for (int i = 0; i <= 2 * DP; ++i) acc[i] = 0.0;
     for (int c0 = 0; c0 < np; c0 += BF_CHUNK) {
         const int nn = c0 + tid;
+        const int krows = (n - c0) < BF_CHUNK ? (n - c0 > 0 ? n - c0 : 0) : BF_CHUNK;       // staged rows beyond n are zero
         double za[DP], wv[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) { za[d] = 0.0; wv[d] = 0.0; }
@@ -369,7 +371,7 @@ __device__ __forceinline__ void mm_bfinish_task(const MMBwdParams& bp, int r, in
         for (int e = tid; e < DP * DP; e += blockDim.x) {           // Omega^r += sum_n za_n[i] w_n[j]
             const int i = e / DP, j = e % DP;
             double v = sOm[e];
-            for (int k = 0; k < BF_CHUNK; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
+            for (int k = 0; k < krows; ++k) v = fma(sRowA[k][i], sRowB[k][j], v);
             sOm[e] = v;
         }
         __syncthreads();

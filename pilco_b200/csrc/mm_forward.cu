@@ -156,7 +156,7 @@ int pilco_mm_forward_taped_profile(const pilco_gp_model* gp, int R, const double
     int rc = mm_check_model(gp);
     if (rc) return rc;
     if (!m || !s || !M || !S || !V || !ws || !tape || !ms_out) return PILCO_ERR_NULL;
-    if (pad64(gp->n) > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
+    if (!mm_tape_supported(gp->n, gp->D)) return PILCO_ERR_UNSUPPORTED;
     if (ws_bytes < pilco_mm_workspace_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
     const MMTapeL TL = mm_tape_layout(gp->n, gp->D, gp->E, R);
     if (tape_bytes < TL.per_r * (size_t)R * sizeof(double)) return PILCO_ERR_WORKSPACE;

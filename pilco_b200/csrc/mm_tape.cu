@@ -8,7 +8,7 @@
 template <int KS>
 static int launch_tape_tile(const MMParams& p, cudaStream_t st) {
     static bool configured_dev[PILCO_MAX_DEVICES] = {false};      // function attributes are per device
-    static int variant = 1;        // 0: <=128 regs; 1: <=96 regs, 2 CTAs/SM; 2: <=80 regs, 2 CTAs/SM (padded smem); 3: <=80 regs, 3 CTAs/SM
+    static int variant = 0;        // 0: <=128 regs (default: fastest tile pass, measured); 1: <=96 regs, 2 CTAs/SM; 2: <=80 regs, 2 CTAs/SM (padded smem); 3: <=80 regs, 3 CTAs/SM
     bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {
         const char* e = getenv("PILCO_TAPE_VARIANT");           // tuning switch
@@ -43,7 +43,7 @@ int mm_tape_tile_launch(const MMParams& p, cudaStream_t st) {
 }
 
 template <int DP>
-__global__ void __launch_bounds__(TB_THREADS, 6) mm_tape_bfinish_kernel(MMTapeBwd bp) {
+__global__ void __launch_bounds__(TB_THREADS, 3) mm_tape_bfinish_kernel(MMTapeBwd bp) {
     PDL_ENTRY();
     extern __shared__ __align__(16) double tb_dyn[];
     mm_tape_bfinish_task<DP>(bp, blockIdx.y, blockIdx.x, tb_dyn);
@@ -64,7 +64,7 @@ int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_redu
     static bool configured_dev[PILCO_MAX_DEVICES] = {false};
     bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {                                          // large n: static + dynamic shared memory > 48 KB
-        const int big = (2 * TAPE_MAX_NP + (TB_WARPS - 1) * 42 * 32) * (int)sizeof(double);
+        const int big = 196 * 1024;
         if (cudaFuncSetAttribute(mm_tape_bfinish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_bfinish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_bfinish_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
@@ -89,7 +89,7 @@ int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_redu
 extern "C" {
 
 size_t pilco_mm_tape_bytes(int n, int D, int E, int R) {
-    if (n < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || R < 1 || pad64(n) > TAPE_MAX_NP) return 0;
+    if (n < 1 || D < 1 || D > MAXD || E < 1 || E > MAXE || R < 1 || !mm_tape_supported(n, D)) return 0;
     return mm_tape_layout(n, D, E, R).per_r * (size_t)R * sizeof(double);
 }
 
@@ -105,7 +105,7 @@ int pilco_mm_forward_taped(const pilco_gp_model* gp, int R, const double* m, con
     if (rc) return rc;
     if (!m || !s || !M || !S || !V || !ws || !tape) return PILCO_ERR_NULL;
     if (R < 1) return PILCO_ERR_DIM;
-    if (pad64(gp->n) > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
+    if (!mm_tape_supported(gp->n, gp->D)) return PILCO_ERR_UNSUPPORTED;
     if (ws_bytes < pilco_mm_workspace_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
     if (tape_bytes < pilco_mm_tape_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
     if ((((uintptr_t)ws) | ((uintptr_t)tape)) & 15) return PILCO_ERR_ALIGN;
@@ -124,7 +124,7 @@ int pilco_mm_backward_taped(const pilco_gp_model* gp, int R, const double* m, co
     if (rc) return rc;
     if (!m || !s || !M || !gM || !gS || !gV || !tape || !gm || !gs || !ws) return PILCO_ERR_NULL;
     if (R < 1) return PILCO_ERR_DIM;
-    if (pad64(gp->n) > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
+    if (!mm_tape_supported(gp->n, gp->D)) return PILCO_ERR_UNSUPPORTED;
     if (tape_bytes < pilco_mm_tape_bytes(gp->n, gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
     if (ws_bytes < pilco_mm_tape_bwd_workspace_bytes(gp->D, gp->E, R)) return PILCO_ERR_WORKSPACE;
     if ((((uintptr_t)ws) | ((uintptr_t)tape)) & 15) return PILCO_ERR_ALIGN;

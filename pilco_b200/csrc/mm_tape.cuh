@@ -33,7 +33,7 @@ static inline __host__ __device__ int mm_tape_splits(int n, int P, int R) {
 static inline __host__ __device__ MMTapeL mm_tape_layout(int n, int D, int E, int R) {
     MMTapeL T;
     T.np = pad64(n); T.P = npairs_of(E);
-    T.ldh = 8 * ((4 * ksteps_of(D) + 7) / 8);
+    T.ldh = ldz_of(D);            // row stride of HZ: 4 / 12 / 20, bank-conflict free as a DMMA B operand (like zeta)
     T.cs = mm_tape_splits(n, T.P, R);
     size_t o = 0;
     auto take = [&](size_t len) { size_t at = o; o += (len + 1) & ~(size_t)1; return at; };
@@ -223,10 +223,11 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
                 }
                 const double hrv = rf[j] * h;
                 if (t == tsum) { tpr[TL.hr + (size_t)q * np + row] = hrv; v = hrv; }
-                double* hzrow = tpr + TL.HZ + ((size_t)q * np + row) * TL.ldh;
+                double* hzrow = tpr + TL.HZ + ((size_t)q * np + row) * ldz;      // (TL.ldh == ldz)
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
-                    *reinterpret_cast<double2*>(hzrow + 8 * nt + 2 * t) = make_double2(rf[j] * hz[j][nt][0], rf[j] * hz[j][nt][1]);
+                    if (8 * nt + 2 * t < ldz)                                    // columns beyond the row stride: not stored
+                        *reinterpret_cast<double2*>(hzrow + 8 * nt + 2 * t) = make_double2(rf[j] * hz[j][nt][0], rf[j] * hz[j][nt][1]);
                 v = warp_sum(v);
             }
             if (lane == 0) p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * NS + oct[j]] = v;
@@ -276,14 +277,23 @@ static inline __host__ __device__ size_t mm_tape_bwd_part_doubles(int D, int E) 
 }
 #define TB_THREADS 128
 #define TB_WARPS 4
-// dynamic shared memory of the finish tasks: per-centre weights [2][np] + the cross-warp reduction buffer [3][NACC][32]
+#define TAPE_MAX_CS 4
+// dynamic shared memory of the finish tasks: per-centre weights u, v [2][np], then the staged tape slice of the pair
+// (HZ [np][ldh] and the column-sum splits [cs][np], fetched by ONE round of TMA bulk copies) which the cross-warp
+// reduction buffer [3][NACC][32] re-uses once the k-loop is over
 static inline __host__ __device__ size_t mm_tape_bfinish_smem_bytes(int np, int D) {
     const int dp = 4 * ksteps_of(D), tx = (dp + 8) / 8;
-    const int nacc = 2 * (tx * (tx + 1) + tx * tx);
-    return ((size_t)2 * np + (size_t)(TB_WARPS - 1) * nacc * 32) * sizeof(double);
+    const size_t nacc = 2 * (tx * (tx + 1) + tx * tx);
+    const size_t stage = (size_t)np * ldz_of(D) + (size_t)TAPE_MAX_CS * np, red = (size_t)(TB_WARPS - 1) * nacc * 32;
+    return ((size_t)2 * np + (stage > red ? stage : red)) * sizeof(double);
 }
 // with_reduce = false: the caller's next kernel sums the task partials itself (mm_tape_reduce_device)
 int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_reduce);
+// shapes the taped path supports: the tile kernel keeps 8 x np column sums, the finish tasks stage a pair's tape slice
+// -- both in shared memory (n <= 1024 centres for D <= 12, <= 704 beyond; larger models use the recomputing sweep)
+static inline __host__ __device__ bool mm_tape_supported(int n, int D) {
+    return pad64(n) <= TAPE_MAX_NP && mm_tape_bfinish_smem_bytes(pad64(n), D) + 24 * 1024 <= 220 * 1024;
+}
 
 #ifdef __CUDACC__
 // sum of the task partials of one restart -> gm [D], gs [D,D] (symmetrised); all threads of the CTA take part.
@@ -296,7 +306,8 @@ __device__ __forceinline__ void mm_tape_reduce_device(const double* __restrict__
         if (e < D) {
             const double* p0 = part + e;
             int tk = 0;
-            for (; tk + 3 < ntask; tk += 4) {
+#pragma unroll 4
+            for (; tk + 3 < ntask; tk += 4) {                        // (unrolled: 16 independent loads in flight)
                 v0 += p0[(size_t)tk * stride]; v1 += p0[(size_t)(tk + 1) * stride];
                 v2 += p0[(size_t)(tk + 2) * stride]; v3 += p0[(size_t)(tk + 3) * stride];
             }
@@ -308,7 +319,8 @@ __device__ __forceinline__ void mm_tape_reduce_device(const double* __restrict__
             const double* p0 = part + MAXD + i * D + j;
             const double* p1 = part + MAXD + j * D + i;
             int tk = 0;
-            for (; tk + 1 < ntask; tk += 2) {
+#pragma unroll 8
+            for (; tk + 1 < ntask; tk += 2) {                        // (unrolled: 32 independent loads in flight)
                 v0 += p0[(size_t)tk * stride]; v1 += p1[(size_t)tk * stride];
                 v2 += p0[(size_t)(tk + 1) * stride]; v3 += p1[(size_t)(tk + 1) * stride];
             }
@@ -348,7 +360,10 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
     __shared__ double sA1[DX * DX], sA2[DX * DX], sA3[DX * DX], sscal[4];
     double* su = tb_dyn;
     double* sv = tb_dyn + np;
-    double* sRed = tb_dyn + 2 * (size_t)np;                    // [(TB_WARPS - 1)][NACC][32] cross-warp reduction
+    double* sHZ = tb_dyn + 2 * (size_t)np;                     // staged HZ slice of the pair [np][ldh] ...
+    double* sHc = sHZ + (size_t)np * TL.ldh;                   // ... and its column-sum splits [cs][np]
+    double* sRed = sHZ;                                        // [(TB_WARPS - 1)][NACC][32]: re-uses the staging area after the k-loop
+    __shared__ __align__(8) uint64_t tbar;
 
     const double* X = gp.X + (size_t)r * gp.X_bs;
     const double* ell = gp.ell + (size_t)r * gp.ell_bs;
@@ -366,8 +381,6 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
     const bool is_out = task < E;
     int a = task, b = task, q = 0;
     const double* HZg = nullptr;
-    const double* hrg = nullptr;
-    const double* hcg = nullptr;
     if (is_out) {
         // ---- output task: W_a = (s + Lambda_a^2)^-1, c_a, per-centre weights u_n = gw_n w_n, v_n = w_n ----
         if (tid < DP) {
@@ -431,9 +444,20 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
             su[nn] = u; sv[nn] = v;
         }
     } else {
-        // ---- pair task: Q, C from the tape; weights u = hr, v = hc (summed over the row splits) ----
+        // ---- pair task: the pair's slice of the tape -- hr, the column-sum splits and HZ -- comes in by ONE round of TMA
+        // bulk copies (the tape was written a whole rollout ago: DRAM-cold; a single bulk round trip instead of a
+        // dependent global load per k-step); Q, C are fetched meanwhile
         q = task - E;
         pair_decode(q, a, b);
+        if (tid == 0) { mbar_init(&tbar, 1); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned bhz = (unsigned)((size_t)n * TL.ldh * 8), bhr = (unsigned)(np * 8), bhc = (unsigned)((size_t)TL.cs * np * 8);
+            mbar_expect_tx(&tbar, bhz + bhr + bhc);
+            tma_bulk_g2s(sHZ, tpr + TL.HZ + (size_t)q * np * TL.ldh, bhz, &tbar);
+            tma_bulk_g2s(su, tpr + TL.hr + (size_t)q * np, bhr, &tbar);
+            tma_bulk_g2s(sHc, tpr + TL.hc + (size_t)q * TL.cs * np, bhc, &tbar);
+        }
         if (tid < DP) {
             const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
             spa[tid] = tid < D ? 1.0 / (la * la) : 0.0;
@@ -447,9 +471,15 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
             sW[i * SLD + j] = in ? Qg[i * D + j] : 0.0;
             sCm[i * SLD + j] = in ? Cg[i * D + j] : 0.0;
         }
-        hrg = tpr + TL.hr + (size_t)q * np;                     // weights u = hr, v = sum of the row splits of hc:
-        hcg = tpr + TL.hc + (size_t)q * TL.cs * np;             // read straight from the tape inside the k-loop
-        HZg = tpr + TL.HZ + (size_t)q * np * TL.ldh;
+        mbar_wait(&tbar, 0);
+        // v = sum of the row splits of the column sums; rows at or beyond n carry no weight (the tile kernel never wrote them)
+        for (int nn = tid; nn < np; nn += blockDim.x) {
+            double v = 0.0;
+            if (nn < n) for (int k = 0; k < TL.cs; ++k) v += sHc[(size_t)k * np + nn];
+            else su[nn] = 0.0;
+            sv[nn] = v;
+        }
+        HZg = sHZ;                                               // (shared memory from here on)
     }
     __syncthreads();
 
@@ -459,41 +489,37 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
     for (int i = 0; i < NSYMT; ++i) { cu[i][0] = cu[i][1] = cv[i][0] = cv[i][1] = 0.0; }
 #pragma unroll
     for (int i = 0; i < TX * TX; ++i) { ch[i][0] = ch[i][1] = 0.0; }
-    // TBU k-steps per trip: all their operands are loaded first (the tape was written a whole rollout ago and comes
-    // from DRAM -- the loads of a trip are independent, so their latencies overlap), then the DMMAs run
-    constexpr int TBU = 2;
+    // TBU k-steps per trip: their centres X (global memory, L2) are fetched first -- independent loads, one round trip
+    // per trip -- then the DMMAs run with the weights and the HZ slice read from shared memory
+    constexpr int TBU = (TX <= 2) ? 8 : 4;
     const int nks = (n + 3) >> 2;
     for (int ks0 = warp; ks0 < nks; ks0 += TB_WARPS * TBU) {
-        double zx[TBU][TX], bh[TBU][TX], uu[TBU], vv[TBU];
+        double zx[TBU][TX];
 #pragma unroll
         for (int k = 0; k < TBU; ++k) {
             const int row = 4 * (ks0 + k * TB_WARPS) + t;
-            const bool live = row < n;                            // (also false for k-steps beyond nks)
-            double uk = 0.0, vk = 0.0;
-            if (live) {
-                if (is_out) { uk = su[row]; vk = sv[row]; }
-                else { uk = hrg[row]; for (int c2 = 0; c2 < TL.cs; ++c2) vk += hcg[(size_t)c2 * np + row]; }
+#pragma unroll
+            for (int tl = 0; tl < TX; ++tl) {
+                const int c = g + 8 * tl;
+                zx[k][tl] = (row < n && c < D) ? X[(size_t)row * D + c] : 0.0;
             }
-            uu[k] = uk; vv[k] = vk;
+        }
+#pragma unroll
+        for (int k = 0; k < TBU; ++k) {
+            const int row = 4 * (ks0 + k * TB_WARPS) + t;
+            if (4 * (ks0 + k * TB_WARPS) >= n) break;             // warp-uniform: no k-step left
+            const bool live = row < n;
+            const double uk = live ? su[row] : 0.0, vk = live ? sv[row] : 0.0;
+            double bu[TX], bv[TX], bh[TX];
 #pragma unroll
             for (int tl = 0; tl < TX; ++tl) {
                 const int c = g + 8 * tl;
                 double z = 0.0, h = 0.0;
                 if (live) {
-                    if (c < D) { z = X[(size_t)row * D + c]; if (HZg) h = HZg[(size_t)row * TL.ldh + c]; }
+                    if (c < D) { z = zx[k][tl] - sm[c]; if (HZg) h = HZg[(size_t)row * TL.ldh + c]; }
                     else if (c == D) z = 1.0;
                 }
-                zx[k][tl] = z; bh[k][tl] = h;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < TBU; ++k) {
-            double bu[TX], bv[TX];
-#pragma unroll
-            for (int tl = 0; tl < TX; ++tl) {
-                const int c = g + 8 * tl;
-                if (c < D) zx[k][tl] -= sm[c];                    // (a dead row has z = 0 and u = v = h = 0: no contribution)
-                bu[tl] = uu[k] * zx[k][tl]; bv[tl] = vv[k] * zx[k][tl];
+                zx[k][tl] = z; bu[tl] = uk * z; bv[tl] = vk * z; bh[tl] = h;
             }
             int si = 0;
 #pragma unroll
@@ -505,11 +531,12 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
                         dmma884(cv[si][0], cv[si][1], zx[k][mt], bv[nt]);
                         ++si;
                     }
-                    if (!is_out) dmma884(ch[mt * TX + nt][0], ch[mt * TX + nt][1], zx[k][mt], bh[k][nt]);
+                    if (!is_out) dmma884(ch[mt * TX + nt][0], ch[mt * TX + nt][1], zx[k][mt], bh[nt]);
                 }
         }
     }
     // cross-warp reduction (fixed order), then warp 0 scatters the C fragments into square matrices
+    __syncthreads();                                           // every warp is done reading the staged slice (sRed aliases it)
     if (warp > 0) {
         double* dst = sRed + ((size_t)(warp - 1) * NACC) * 32 + lane;
         int k = 0;

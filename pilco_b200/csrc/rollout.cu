@@ -151,7 +151,7 @@ size_t pilco_rollout_workspace_bytes(const pilco_rollout* ro) {
 
 size_t pilco_rollout_tape_bytes(const pilco_rollout* ro) {
     if (!ro || ro->R < 1 || ro->H < 0) return 0;
-    if (pad64(ro->dyn.n) > TAPE_MAX_NP || ro->dyn.D < 1 || ro->dyn.D > MAXD || ro->dyn.E < 1 || ro->dyn.E > MAXE) return 0;
+    if (!mm_tape_supported(ro->dyn.n, ro->dyn.D) || ro->dyn.D < 1 || ro->dyn.D > MAXD || ro->dyn.E < 1 || ro->dyn.E > MAXE) return 0;
     return mm_tape_layout(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R).per_r * (size_t)ro->R * (size_t)ro->H * sizeof(double);
 }
 

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(128) rb_post_kernel(RbDev p) {
 
 // taped path: dynamics VJP from the tape + (last CTA of the restart) rb_post, ONE launch per step
 template <int DP>
-__global__ void __launch_bounds__(TB_THREADS, 6) rb_dyn_finish_kernel(MMTapeBwd bp, RbDev d) {
+__global__ void __launch_bounds__(TB_THREADS, 3) rb_dyn_finish_kernel(MMTapeBwd bp, RbDev d) {
     PDL_ENTRY();
     extern __shared__ __align__(16) unsigned char rb_dyn_smem[];
     const int r = blockIdx.y;
@@ -239,7 +239,7 @@ static int launch_dyn_finish(const MMTapeBwd& tb, const RbDev& d, cudaStream_t s
     static bool configured_dev[PILCO_MAX_DEVICES] = {false};
     bool& configured = configured_dev[pilco_current_device()];
     if (!configured) {
-        const int big = (int)mm_tape_bfinish_smem_bytes(TAPE_MAX_NP, MAXD);
+        const int big = 196 * 1024;
         if (cudaFuncSetAttribute(rb_dyn_finish_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess) return PILCO_ERR_LAUNCH;
         configured = true;
     }

@@ -267,7 +267,7 @@ def mm_forward_taped(gp, m, s):
     ws = torch.empty(wsb // 8, dtype=F64, device=d)
     tb = lib.pilco_mm_tape_bytes(gp.n, gp.D, gp.E, R)
     if tb == 0:
-        raise ValueError("taped moment match supports at most 2048 centres (got %d)" % gp.n)
+        raise ValueError("taped moment match: %d centres (D=%d) exceed what its shared-memory staging holds (n <= 1024 for D <= 12)" % (gp.n, gp.D))
     tape = torch.empty(tb // 8, dtype=F64, device=d)
     g = gp.struct()
     check(lib.pilco_mm_forward_taped(C.byref(g), R, ptr(m), ptr(s), ptr(M), ptr(S), ptr(V), ptr(info),

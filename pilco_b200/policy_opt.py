@@ -22,9 +22,16 @@ LAST_STATS = {}          # filled by optimize(): evaluator calls, restarts on th
 
 
 class PolicyEvaluator:
-    """loss(flat) = -sum_t E[r(x_t)] and its gradient for a batch of flat policy parameter vectors."""
+    """loss(flat) = -sum_t E[r(x_t)] and its gradient for a batch of flat policy parameter vectors.
 
-    def __init__(self, pilco, R):
+    The R restarts are dealt to ``nsplit`` sub-batches, each with its own RolloutPlan (taped forward + reverse sweep)
+    on its own stream inside ONE captured CUDA graph: the latency-bound glue kernels of one sub-batch overlap the tile
+    kernels of the others (measured at the metric shape, R = 32: 40.5 k / 43.3 k / 46.0 k rollout steps/s forward +
+    backward with 1 / 2 / 4 sub-batches; 8 is slower for the reverse sweep)."""
+
+    NSPLIT = 4
+
+    def __init__(self, pilco, R, nsplit=None):
         self.pilco, self.R = pilco, R
         c = pilco.controller
         self.c = c
@@ -33,18 +40,23 @@ class PolicyEvaluator:
         self.P = flat0.shape[1]
         if self.linear:
             U, Ds = c.W.shape
-            spec = c.policy_spec(flat0)
         else:
             bf, Ds, U = c.policy_shapes
-            spec = pilco.policy_spec(flat0)
-            self.gp = spec["gp"]
             self.ell_lower = float(c.models[0].kernel.lengthscales.transform.lower)
         self.shape = (Ds, U)
         terms, mult_mu = pilco.reward_spec()
-        self.plan = engine.RolloutPlan(pilco.mgpr.device_gp(), spec, terms,
-                                       np.asarray(pilco.m_init, dtype=np.float64).reshape(-1),
-                                       np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=R,
-                                       mult_mu=mult_mu, grad=True)
+        nsplit = max(1, min(int(self.NSPLIT if nsplit is None else nsplit), R // 4 if R >= 8 else 1))
+        bounds = [round(k * R / nsplit) for k in range(nsplit + 1)]
+        self.slices = [(bounds[k], bounds[k + 1]) for k in range(nsplit) if bounds[k + 1] > bounds[k]]
+        self.plans, self.gps = [], []
+        dyn = pilco.mgpr.device_gp()
+        for lo, hi in self.slices:
+            spec = c.policy_spec(flat0[lo:hi]) if self.linear else pilco.policy_spec(flat0[lo:hi])
+            self.gps.append(None if self.linear else spec["gp"])
+            self.plans.append(engine.RolloutPlan(dyn, spec, terms, np.asarray(pilco.m_init, dtype=np.float64).reshape(-1),
+                                                 np.asarray(pilco.S_init, dtype=np.float64), int(pilco.horizon), R=hi - lo,
+                                                 mult_mu=mult_mu, grad=True))
+        self.side = [torch.cuda.Stream() for _ in self.plans[1:]]
         self.h_flat = torch.empty((R, self.P), dtype=torch.float64).pin_memory()
         self.h_out = torch.empty((R, self.P + 2), dtype=torch.float64).pin_memory()
         self.d_flat = torch.empty((R, self.P), dtype=torch.float64, device=engine.device())
@@ -79,37 +91,48 @@ class PolicyEvaluator:
     use_graph = True
 
     def _enqueue(self):
-        R, P = self.R, self.P
-        Ds, U = self.shape
         self.d_flat.copy_(self.h_flat, non_blocking=True)
-        plan = self.plan
+        cur = torch.cuda.current_stream()
+        for st in self.side:                                   # fork: sub-batch k >= 1 on its own stream
+            st.wait_stream(cur)
+        self._enqueue_slice(0)
+        for k, st in enumerate(self.side, start=1):
+            with torch.cuda.stream(st):
+                self._enqueue_slice(k)
+        for st in self.side:                                   # join
+            cur.wait_stream(st)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def _enqueue_slice(self, k):
+        (lo, hi), plan, gp = self.slices[k], self.plans[k], self.gps[k]
+        R = hi - lo
+        Ds, U = self.shape
+        flat = self.d_flat[lo:hi]
         if self.linear:
-            plan.W.copy_(self.d_flat[:, :U * Ds].reshape(R, U, Ds))
-            plan.b.copy_(self.d_flat[:, U * Ds:].reshape(R, U))
+            plan.W.copy_(flat[:, :U * Ds].reshape(R, U, Ds))
+            plan.b.copy_(flat[:, U * Ds:].reshape(R, U))
         else:
-            gp = self.gp
             bf = gp.n
-            th = self.d_flat[:, bf * Ds + bf * U:].reshape(R, U, Ds)
-            gp.X.copy_(self.d_flat[:, :bf * Ds].reshape(R, bf, Ds))
-            gp.Y.copy_(self.d_flat[:, bf * Ds:bf * Ds + bf * U].reshape(R, bf, U))
+            th = flat[:, bf * Ds + bf * U:].reshape(R, U, Ds)
+            gp.X.copy_(flat[:, :bf * Ds].reshape(R, bf, Ds))
+            gp.Y.copy_(flat[:, bf * Ds:bf * Ds + bf * U].reshape(R, bf, U))
             # ell = lower + log(1 + e^theta): the controller's own transform (controllers.py:100), same formula as
             # params.Softplus.forward on the host (np.logaddexp)
             gp.ell.copy_(self.ell_lower + torch.logaddexp(th, torch.zeros_like(th)))
             engine.gp_refactorize(gp)
         plan.forward()
         g = plan.backward()
-        out = self.d_out
+        out = self.d_out[lo:hi]
         out[:, 0] = -plan.reward
         out[:, 1] = torch.maximum(plan.info, gp.info if not self.linear else plan.info).to(torch.float64)
         if self.linear:
             out[:, 2:2 + U * Ds] = -g["W"].reshape(R, -1)
             out[:, 2 + U * Ds:] = -g["b"].reshape(R, -1)
         else:
-            bf = self.gp.n
+            bf = gp.n
             out[:, 2:2 + bf * Ds] = -g["X"].reshape(R, -1)
             out[:, 2 + bf * Ds:2 + bf * Ds + bf * U] = -g["Y"].reshape(R, -1)
             out[:, 2 + bf * Ds + bf * U:] = -(g["ell"] * torch.sigmoid(th)).reshape(R, -1)
-        self.h_out.copy_(out, non_blocking=True)
 
 
 class LockstepLBFGS:
