@@ -771,12 +771,32 @@ def main():
     ap.add_argument("--maxiter", type=int, default=10, help="--through-api: L-BFGS-B iterations")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
-    if args.impl == "reference":
-        run_reference(args, cfg)
-    elif args.through_api:
-        run_through_api(args, cfg)
-    else:
-        run_ours(args, cfg)
+    # Exactly ONE line on stdout (the JSON): everything any library writes to file descriptor 1 meanwhile (NCCL's
+    # "NCCL version ..." banner is written by C code, not through sys.stdout) is sent to stderr; the JSON line is
+    # printed through the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def print_json(*a, **k):
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
+    g = globals()
+    g["print"] = print_json                                  # the run_* functions print only the JSON line
+    try:
+        if args.impl == "reference":
+            run_reference(args, cfg)
+        elif args.through_api:
+            run_through_api(args, cfg)
+        else:
+            run_ours(args, cfg)
+    finally:
+        g.pop("print", None)
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
