@@ -11,7 +11,7 @@ python bench.py --impl reference --steps 20 --warmup 3 > $OUT/bench_metric_refer
 kill $SMI
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_fwd_bwd.csv python scripts/profile_step.py --H 3 > $OUT/p_launch.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $OUT/launches_fwd_r1.csv python scripts/profile_step.py --R 1 --H 3 --no-backward > $OUT/p_launch_r1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mm_tile_kernel -s 6 -c 1 -o $OUT/mm_tile python scripts/profile_step.py --H 2 --no-backward > $OUT/p_tile.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:mm_tile_kernel -s 5 -c 1 -o $OUT/mm_tile python scripts/profile_step.py --H 2 --no-backward > $OUT/p_tile.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mm_tape_tile -s 3 -c 1 -o $OUT/mm_tape_tile python scripts/profile_step.py --H 2 > $OUT/p_tape.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rb_dyn_finish -s 2 -c 1 -o $OUT/rb_dyn_finish python scripts/profile_step.py --H 2 > $OUT/p_fin.log 2>&1
 ls -la $OUT
