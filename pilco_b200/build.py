@@ -64,8 +64,17 @@ def build(force=False, verbose=False, extra_flags=(), lib=None, build_dir=None):
     return out_lib
 
 
+def build_exp256(force=True):
+    """Variant library with the bank-conflict-free 256 x 16 exp table (-DPILCO_EXP256), beside the product library:
+    select it with PILCO_B200_LIB=<path> (A/B measurements)."""
+    return build(force=force, extra_flags=["-DPILCO_EXP256"], lib=os.path.join(HERE, "build_exp256", "libpilco_b200_exp256.so"),
+                 build_dir=os.path.join(HERE, "build_exp256"))
+
+
 if __name__ == "__main__":
-    if "--timing" in sys.argv:      # diagnostics variant with per-CTA phase stamps in the tile kernel
+    if "--exp256" in sys.argv:
+        print(build_exp256())
+    elif "--timing" in sys.argv:      # diagnostics variant with per-CTA phase stamps in the tile kernel
         print(build(force=True, extra_flags=["-DPILCO_TILE_TIMING"], lib=os.path.join(HERE, "build_timing", "libpilco_b200_timing.so"),
                     build_dir=os.path.join(HERE, "build_timing")))
     else:

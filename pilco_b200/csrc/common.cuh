@@ -19,6 +19,7 @@
 #define MAXD PILCO_MAX_D
 #define MAXE PILCO_MAX_E
 #define SLD  17                 // leading dimension of small smem matrices (odd -> conflict-light)
+#define PILCO_MAX_SMEM_OPTIN (227 * 1024)   // dynamic shared memory a CTA can opt in to on sm_100
 #define NEG_PAD (-1.0e9)        // (scaled) exponent of padded rows/cols: exp_scaled() clamps it to ~1e-304
 
 #define CUDA_LAUNCH_CHECK() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return PILCO_ERR_LAUNCH; } while (0)
@@ -185,8 +186,12 @@ __device__ __forceinline__ void lu_solve_warp(const double* LU, const int* perm,
 // table T[j] = 2^(j/EXP_TAB), correctly rounded (scripts/gen_exp_table.py), compiled into the library: no run-time
 // upload, no per-device state, so every entry point is CUDA-graph capturable from its first call
 // (one copy per translation unit: the library is built without relocatable device code)
-static __device__ __align__(16) const double g_exp_tab[EXP_TAB] = {
+static __device__ __align__(16) const double g_exp_tab[EXP_TAB_DOUBLES] = {
+#ifdef PILCO_EXP256
+#include "exp_table_data256x16.inc"
+#else
 #include "exp_table_data.inc"
+#endif
 };
 #define PILCO_MAX_DEVICES 64
 static inline int pilco_current_device() {
@@ -274,7 +279,7 @@ static inline bool pilco_small_grid(dim3 g) { return (long long)g.x * g.y * g.z 
 #endif       // (kept for the launchers: nothing to upload)
 
 __device__ __forceinline__ void exp_table_init(double* tab) {
-    for (int j = threadIdx.x; j < EXP_TAB; j += blockDim.x) tab[j] = g_exp_tab[j];
+    for (int j = threadIdx.x; j < EXP_TAB_DOUBLES; j += blockDim.x) tab[j] = g_exp_tab[j];
 }
 
 // (exp_scaled, exp_shifted, exp_row_split: exp_table.cuh -- shared with the host test build)

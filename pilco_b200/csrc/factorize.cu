@@ -239,13 +239,163 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs g) {
         }
 }
 
+// fp64 tensor-core variant (round 2): same contract, CTA tile 64 x 64, K tile 16, 8 warps as 4 (m) x 2 (n), warp tile
+// 16 x 32 = 2 x 4 DMMA.8x8x4 accumulators.  Operand tiles staged K-major in shared memory with row stride 68
+// (= 4 mod 16: the DMMA fragment reads of a half-warp hit 16 distinct bank pairs).  Used for every product of the
+// factorisations and training objectives (iK = L^-T L^-1, FITC V V', B = V diag(1/nu) V', block-inverse updates ...).
+#define GD_LD 68
+__global__ void __launch_bounds__(256) gemm_dmma_kernel(GemmArgs g) {
+    PDL_ENTRY();
+    __shared__ double sA[16][GD_LD];
+    __shared__ double sB[16][GD_LD];
+    const double* A = g.A + (size_t)blockIdx.z * g.sa;
+    const double* B = g.B + (size_t)blockIdx.z * g.sb;
+    double* C = g.C + (size_t)blockIdx.z * g.sc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;      // warp tile origin inside the CTA tile
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    double acc[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+    for (int k0 = 0; k0 < g.k; k0 += 16) {
+        for (int e = tid; e < 16 * 64; e += 256) {
+            int kk, ii;
+            if (g.ta) { ii = e % 64; kk = e / 64; } else { kk = e % 16; ii = e / 16; }
+            const int gi = i0 + ii, gk = k0 + kk;
+            double v = 0.0;
+            if (gi < g.m && gk < g.k) v = g.ta ? A[(size_t)gk * g.lda + gi] : A[(size_t)gi * g.lda + gk];
+            sA[kk][ii] = v;
+        }
+        for (int e = tid; e < 16 * 64; e += 256) {
+            int kk, jj;
+            if (g.tb) { kk = e % 16; jj = e / 16; } else { jj = e % 64; kk = e / 64; }
+            const int gj = j0 + jj, gk = k0 + kk;
+            double v = 0.0;
+            if (gj < g.n && gk < g.k) v = g.tb ? B[(size_t)gj * g.ldb + gk] : B[(size_t)gk * g.ldb + gj];
+            sB[kk][jj] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) af[a] = sA[4 * ks + t][wm + 8 * a + gq];     // A[m = row gq][k = t]
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = sB[4 * ks + t][wn + 8 * b + gq];     // B[k = t][n = col gq]
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int gi = i0 + wm + 8 * a + gq, gj = j0 + wn + 8 * b + 2 * t + c;     // C[row gq][cols 2t, 2t+1]
+                if (gi < g.m && gj < g.n) {
+                    double* cp = C + (size_t)gi * g.ldc + gj;
+                    *cp = g.alpha * acc[a][b][c] + (g.beta != 0.0 ? g.beta * (*cp) : 0.0);
+                }
+            }
+}
+
 static int gemm(cudaStream_t st, int batch, int m, int n, int k, int ta, int tb, double alpha,
                 const double* A, int lda, long long sa, const double* B, int ldb, long long sb,
                 double beta, double* C, int ldc, long long sc) {
     if (m <= 0 || n <= 0) return PILCO_OK;
     GemmArgs g{m, n, k, ta, tb, alpha, beta, A, lda, sa, B, ldb, sb, C, ldc, sc};
     dim3 grid((n + 63) / 64, (m + 63) / 64, batch);
-    gemm_kernel<<<grid, 256, 0, st>>>(g);
+    static int use_dmma = -1;                                   // PILCO_GEMM_DFMA=1: the round-1 DFMA kernel (A/B switch)
+    if (use_dmma < 0) { const char* e = getenv("PILCO_GEMM_DFMA"); use_dmma = (e && e[0] == '1') ? 0 : 1; }
+    if (use_dmma) launch_pri(pilco_small_grid(grid), gemm_dmma_kernel, grid, dim3(256), 0, st, g);
+    else gemm_kernel<<<grid, 256, 0, st>>>(g);
+    CUDA_LAUNCH_CHECK();
+    return PILCO_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Cholesky at scale (round 2): for n >= CHOL_MULTI_N the right-looking blocked algorithm runs ACROSS CTAs -- per block
+// column: diagonal block (one CTA per matrix), panel solve (one thread per row, 256 rows per CTA), trailing update
+// A22 -= L21 L21' as ONE batched DMMA GEMM over the whole remaining square (the upper half is redundant work, but it
+// is tensor-core work spread over the machine instead of 64 x 64 DFMA tiles on the single CTA of chol_kernel).
+// -------------------------------------------------------------------------------------------------
+#define CHOL_MULTI_N 512
+__global__ void __launch_bounds__(32) chol_diag_kernel(int n, int k0, double* Aall, int ld, long long ms, int mats_per_b, int* info) {
+    PDL_ENTRY();
+    __shared__ double sD[FB][FB + 1];
+    double* A = Aall + (size_t)blockIdx.x * ms;
+    const int lane = threadIdx.x, kb = min(FB, n - k0);
+    for (int i = 0; i < FB; ++i) sD[i][lane] = (i < kb && lane < kb) ? A[(size_t)(k0 + i) * ld + k0 + lane] : (i == lane ? 1.0 : 0.0);
+    __syncwarp();
+    bool fail = false;
+    for (int j = 0; j < kb; ++j) {                              // left-looking, lane = row (as in chol_kernel)
+        double v = sD[lane][j];
+        for (int k = 0; k < j; ++k) v = fma(-sD[lane][k], sD[j][k], v);
+        double piv = __shfl_sync(0xffffffffu, v, j);
+        if (!(piv > 0.0)) { fail = true; piv = 1.0; }
+        const double rp = 1.0 / sqrt(piv);
+        __syncwarp();
+        if (lane >= j) sD[lane][j] = (lane == j) ? sqrt(piv) : v * rp;
+        __syncwarp();
+    }
+    for (int i = 0; i < kb; ++i) if (lane < kb) A[(size_t)(k0 + i) * ld + k0 + lane] = (lane <= i) ? sD[i][lane] : 0.0;
+    if (lane == 0 && fail && info) atomicOr(&info[blockIdx.x / mats_per_b], 2);
+}
+__global__ void __launch_bounds__(256) chol_panel_kernel(int n, int k0, double* Aall, int ld, long long ms) {
+    PDL_ENTRY();
+    __shared__ double sD[FB][FB + 1];
+    double* A = Aall + (size_t)blockIdx.y * ms;
+    const int tid = threadIdx.x, kb = min(FB, n - k0);
+    for (int e = tid; e < FB * FB; e += 256) {
+        const int i = e / FB, j = e % FB;
+        sD[i][j] = (i < kb && j < kb) ? A[(size_t)(k0 + i) * ld + k0 + j] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    const int i = k0 + kb + blockIdx.x * 256 + tid;
+    if (i >= n) return;
+    double x[FB];
+    double* arow = A + (size_t)i * ld + k0;
+#pragma unroll
+    for (int j = 0; j < FB; ++j) x[j] = j < kb ? arow[j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < FB; ++j) {
+        if (j < kb) {
+            double v = x[j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v = fma(-x[k], sD[j][k], v);
+            x[j] = v / sD[j][j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < FB; ++j) if (j < kb) arow[j] = x[j];
+}
+__global__ void __launch_bounds__(256) chol_kernel(int n, double* Aall, int ld, long long ms, int mats_per_b, int* info);
+// in-place lower Cholesky of `batch` matrices (info index = matrix / mats_per_b): one CTA per matrix when small
+static int chol_launch(cudaStream_t st, int batch, int n, double* A, int ld, long long ms, int mats_per_b, int* info) {
+    static int single = -1;                                     // PILCO_CHOL_SINGLE=1: always the one-CTA kernel (A/B switch)
+    if (single < 0) { const char* e = getenv("PILCO_CHOL_SINGLE"); single = (e && e[0] == '1') ? 1 : 0; }
+    if (n < CHOL_MULTI_N || single) {
+        launch_hi(chol_kernel, dim3(batch), dim3(256), 0, st, n, A, ld, ms, mats_per_b, info);
+        CUDA_LAUNCH_CHECK();
+        return PILCO_OK;
+    }
+    for (int k0 = 0; k0 < n; k0 += FB) {
+        const int kb = min(FB, n - k0), t0 = k0 + kb;
+        launch_hi(chol_diag_kernel, dim3(batch), dim3(32), 0, st, n, k0, A, ld, ms, mats_per_b, info);
+        if (t0 >= n) break;
+        launch_hi(chol_panel_kernel, dim3((n - t0 + 255) / 256, batch), dim3(256), 0, st, n, k0, A, ld, ms);
+        CUDA_LAUNCH_CHECK();
+        const double* P = A + (size_t)t0 * ld + k0;              // L21 [n - t0, kb]
+        int rc = gemm(st, batch, n - t0, n - t0, kb, 0, 1, -1.0, P, ld, ms, P, ld, ms, 1.0, A + (size_t)t0 * ld + t0, ld, ms);
+        if (rc) return rc;
+    }
     CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }
@@ -424,7 +574,7 @@ int pilco_gp_factorize(int n, int D, int E, int B,
     GramArgs g{n, n, D, E, X, X_bs, X, X_bs, ell, ell_bs, sf2, sf2_bs, sn2, sn2_bs, 0.0, L, ldw, ms, ldw, ldw, 0};
     launch_hi(gram_kernel, dim3((ldw + 31) / 32, (ldw + 7) / 8, batch), dim3(32, 8), 0, st, g);
     CUDA_LAUNCH_CHECK();
-    launch_hi(chol_kernel, dim3(batch), dim3(256), 0, st, n, L, ldw, ms, E, info);
+    { int rcc = chol_launch(st, batch, n, L, ldw, ms, E, info); if (rcc) return rcc; }
     CUDA_LAUNCH_CHECK();
     // beta = (L L^T)^-1 y_e   (mgpr.py:86-88)
     launch_hi(chol_solve_vec_kernel, dim3(batch), dim3(256), n * sizeof(double), st, n, L, ldw, ms, E, Y, Y_bs, 1, E, beta, n);
@@ -510,7 +660,7 @@ extern "C" int pilco_gp_append(int n0, int k, int D, int E,
     if (rc) return rc;
     rc = gemm(st, E, k, k, n0, 0, 1, -1.0, F, ld0, rs, K21, ld0, rs, 1.0, S, kp, qs);                        // S -= F K12
     if (rc) return rc;
-    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, k, S, kp, qs, E, info);
+    { int rcc = chol_launch(st, E, k, S, kp, qs, E, info); if (rcc) return rcc; }
     CUDA_LAUNCH_CHECK();
     cudaMemsetAsync(Li, 0, (size_t)E * qs * sizeof(double), st);
     rc = tri_inverse(st, E, k, S, kp, qs, Li, kp, qs, T, (long long)FB * kp);
@@ -815,7 +965,7 @@ int pilco_fitc_nlml(int N, int Mi, int D, int E, int B,
     GramArgs guf{Mi, N, D, 1, Z, (long long)Mi * D, X, 0, ell, D, sf2, 1, nullptr, 0, 0.0, w + W.Kuf, ldn, zs, Mi, N, 0};
     launch_hi(gram_kernel, dim3((N + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st, guf);
     CUDA_LAUNCH_CHECK();
-    launch_hi(chol_kernel, dim3(Zb), dim3(256), 0, st, Mi, w + W.Luu, ldm, zs, E, info);
+    { int rcc = chol_launch(st, Zb, Mi, w + W.Luu, ldm, zs, E, info); if (rcc) return rcc; }
     tri_op_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st>>>(Mi, w + W.Luu, ldm, zs, 0);     // strict upper := 0
     CUDA_LAUNCH_CHECK();
     int rc = tri_inverse(st, Zb, Mi, w + W.Luu, ldm, zs, w + W.LinvU, ldm, zs, w + W.Ts, zs);
@@ -827,7 +977,7 @@ int pilco_fitc_nlml(int N, int Mi, int D, int E, int B,
     rc = gemm(st, Zb, Mi, Mi, N, 0, 1, 1.0, w + W.T1, ldn, zs, w + W.V, ldn, zs, 0.0, w + W.Bm, ldm, zs);            // V diag(1/nu) V'
     if (rc) return rc;
     add_diag_const_kernel<<<dim3((Mi + 127) / 128, Zb), 128, 0, st>>>(Mi, w + W.Bm, ldm, zs, 1.0);
-    launch_hi(chol_kernel, dim3(Zb), dim3(256), 0, st, Mi, w + W.Bm, ldm, zs, E, info);                          // L (in Bm)
+    { int rcc = chol_launch(st, Zb, Mi, w + W.Bm, ldm, zs, E, info); if (rcc) return rcc; }                          // L (in Bm)
     tri_op_kernel<<<dim3((Mi + 31) / 32, (Mi + 7) / 8, Zb), dim3(32, 8), 0, st>>>(Mi, w + W.Bm, ldm, zs, 0);
     CUDA_LAUNCH_CHECK();
     rc = tri_inverse(st, Zb, Mi, w + W.Bm, ldm, zs, w + W.LinvB, ldm, zs, w + W.Ts, zs);
@@ -891,7 +1041,7 @@ int pilco_fitc_factorize(int N, int Mi, int D, int E, const double* X, const dou
     GramArgs gmn{Mi, N, D, E, Z, 0, X, 0, ell, 0, sf2, 0, nullptr, 0, 0.0, Vg, ldn, mn, Mi, N, 0};
     launch_hi(gram_kernel, dim3((N + 31) / 32, (Mi + 7) / 8, E), dim3(32, 8), 0, st, gmn);     // Kmn -> Vg (temp)
     CUDA_LAUNCH_CHECK();
-    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, Mi, L, ldm, mm, E, info);                            // L = chol(Kmm)  :29
+    { int rcc = chol_launch(st, E, Mi, L, ldm, mm, E, info); if (rcc) return rcc; }                            // L = chol(Kmm)  :29
     CUDA_LAUNCH_CHECK();
     int rc = tri_inverse(st, E, Mi, L, ldm, mm, Linv, ldm, mm, T, mm);                   // Linv = L^-1
     if (rc) return rc;
@@ -903,7 +1053,7 @@ int pilco_fitc_factorize(int N, int Mi, int D, int E, const double* X, const dou
     if (rc) return rc;
     add_diag_kernel<<<dim3((Mi + 127) / 128, E), 128, 0, st>>>(Mi, Am, ldm, mm, sn2);    // + sn2 I   :34-35
     CUDA_LAUNCH_CHECK();
-    launch_hi(chol_kernel, dim3(E), dim3(256), 0, st, Mi, Am, ldm, mm, E, info);                           // Am
+    { int rcc = chol_launch(st, E, Mi, Am, ldm, mm, E, info); if (rcc) return rcc; }                           // Am
     CUDA_LAUNCH_CHECK();
     fill(st, T, (size_t)E * mm, 0.0);
     rc = tri_inverse(st, E, Mi, Am, ldm, mm, Aminv, ldm, mm, T, mm);                     // Am^-1

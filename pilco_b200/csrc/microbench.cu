@@ -6,9 +6,10 @@
 
 template <int WHICH>
 __global__ void __launch_bounds__(256) fp64_pipe_kernel(int iters, double* sink) {
-    __shared__ double tab[EXP_TAB];
+    __shared__ double tab[EXP_TAB_DOUBLES];
     exp_table_init(tab);
     __syncthreads();
+    const double* ltab = EXP_LANE_TAB(tab, threadIdx.x);
     const double seed = 1.0 + 1e-9 * threadIdx.x;
     double a0 = seed, a1 = seed * 1.1, a2 = seed * 1.2, a3 = seed * 1.3, a4 = seed * 1.4, a5 = seed * 1.5, a6 = seed * 1.6, a7 = seed * 1.7;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
@@ -26,8 +27,8 @@ __global__ void __launch_bounds__(256) fp64_pipe_kernel(int iters, double* sink)
             if (WHICH == 1) { a0 += c1 * 1e-300; a3 += c2 * 1e-300; }
         }
         if (WHICH == 3) {
-            a0 = exp_scaled(a0 - 300.0, tab); a1 = exp_scaled(a1 - 311.1, tab); a2 = exp_scaled(a2 - 322.2, tab); a3 = exp_scaled(a3 - 333.3, tab);
-            a4 = exp_scaled(a4 - 344.4, tab); a5 = exp_scaled(a5 - 355.5, tab); a6 = exp_scaled(a6 - 366.6, tab); a7 = exp_scaled(a7 - 377.7, tab);
+            a0 = exp_scaled(a0 - 300.0, ltab); a1 = exp_scaled(a1 - 311.1, ltab); a2 = exp_scaled(a2 - 322.2, ltab); a3 = exp_scaled(a3 - 333.3, ltab);
+            a4 = exp_scaled(a4 - 344.4, ltab); a5 = exp_scaled(a5 - 355.5, ltab); a6 = exp_scaled(a6 - 366.6, ltab); a7 = exp_scaled(a7 - 377.7, ltab);
         }
         if (WHICH == 4) {
             a0 = exp(a0 - 1.0); a1 = exp(a1 - 1.1); a2 = exp(a2 - 1.2); a3 = exp(a3 - 1.3);

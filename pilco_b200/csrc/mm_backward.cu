@@ -14,7 +14,7 @@
 // -------------------------------------------------------------------------------------------------
 static inline __host__ __device__ size_t mm_btile_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
-    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
+    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB_DOUBLES * 8 + 16;
 }
 
 // DIAG = true : grid (NB, E, R), the pairs (a,a) of a GP with trace term (iK-weighted sums as well);
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     double* sBq = sZ + (size_t)CM * ldz;
     double* sBe = sBq + CM;
     double* tab = sBe + CM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB_DOUBLES);
 
     const int r = blockIdx.z, rb = blockIdx.x;
     const bool has_trace = (p.gp.mode == 0) && (p.gp.iK != nullptr);
@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     double* wsr = p.ws + (size_t)r * bp.B.per_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+    const double* ltab = EXP_LANE_TAB(tab, lane);
     const int row0 = rb * 64 + warp * 8;
     const int row = row0 + g;
     const bool active = row0 < p.gp.n;
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
     auto issue_chunk = [&](int c0, bool with_table) {
         const int cm = (np - c0) < CM ? (np - c0) : CM;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB * 8 : 0)));
+        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB_DOUBLES * 8 : 0)));
         tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
         tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
         tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
-        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB_DOUBLES * 8), bar);
     };
     if (tid == 0) issue_chunk(0, true);
     double ua[KS], Apv;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(256, DIAG ? 2 : 4) mm_btile_kernel(MMBwdParams
                     const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
                     dmma884(e0, e1, ua[ks], bf);
                 }
-                const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
+                const double l0 = exp_shifted(e0, am, ltab), l1 = exp_shifted(e1, am, ltab);
                 const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                 const double w0 = bb.x * l0, w1 = bb.y * l1;        // W[g][2t], W[g][2t+1]  (C-fragment layout)
                 hl += w0 + w1;

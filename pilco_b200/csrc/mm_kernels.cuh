@@ -579,7 +579,7 @@ static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
 // -------------------------------------------------------------------------------------------------
 static inline __host__ __device__ size_t mm_tile_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
-    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16;
+    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB_DOUBLES * 8 + 16;
 }
 // one partial per row octet (= per warp of a tile CTA): warps retire independently, no block reduction
 static inline __host__ __device__ int mm_tile_slots(int np) { return np / 8; }
@@ -608,7 +608,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
     double* sBq = sZ + (size_t)CM * ldz;
     double* sBe = sBq + CM;
     double* tab = sBe + CM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB_DOUBLES);
 
     // this CTA: pair q of restart r, row blocks [rb0, rb1) swept one after the other (the staged columns, the exp
     // table and the barrier are set up once per CTA; only the row operands change between passes)
@@ -620,6 +620,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
     const double* wsr = p.ws + (size_t)r * L.per_r;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+    const double* ltab = EXP_LANE_TAB(tab, lane);      // this lane's copy of the exp table (conflict-free gather)
     const int ncol8 = (n + 7) & ~7;                    // columns at or beyond this are pure padding
     constexpr bool sympair = SYM;                      // symmetric pair (a == b): visit the upper triangle only
     constexpr bool diag = DIAG;                        // ... and (exact-GP mode) subtract the trace term
@@ -634,11 +635,11 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
         const int cm = (np - c0) < CM ? (np - c0) : CM;
         const int ncopy = cm - lo;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_expect_tx(bar, (unsigned)(ncopy * ldz * 8 + ncopy * 16 + (with_table ? EXP_TAB * 8 : 0)));
+        mbar_expect_tx(bar, (unsigned)(ncopy * ldz * 8 + ncopy * 16 + (with_table ? EXP_TAB_DOUBLES * 8 : 0)));
         tma_bulk_g2s(sZ + (size_t)lo * ldz, wsr + L.zeta + (size_t)(c0 + lo) * ldz, (unsigned)(ncopy * ldz * 8), bar);
         tma_bulk_g2s(sBq + lo, wsr + L.Bq + (size_t)q * np + c0 + lo, (unsigned)(ncopy * 8), bar);
         tma_bulk_g2s(sBe + lo, wsr + L.betap + (size_t)b * np + c0 + lo, (unsigned)(ncopy * 8), bar);
-        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB_DOUBLES * 8), bar);
     };
     {
         const int cfirst0 = sympair ? rb0 * 64 : 0;
@@ -718,7 +719,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const double l0 = exp_shifted(e[2 * j], am, tab), l1 = exp_shifted(e[2 * j + 1], am, tab);
+                            const double l0 = exp_shifted(e[2 * j], am, ltab), l1 = exp_shifted(e[2 * j + 1], am, ltab);
                             const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
                             acc2 = fma(bb.x, l0, acc2); acc2 = fma(bb.y, l1, acc2);
                             if (diag) { tr2 = fma(ik[j].x, l0, tr2); tr2 = fma(ik[j].y, l1, tr2); }
@@ -737,7 +738,7 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
                                 const double bf = sZ[(size_t)(col + g) * ldz + 4 * ks + t];
                                 dmma884(e0, e1, ua[ks], bf);
                             }
-                            const double l0 = exp_shifted(e0, am, tab), l1 = exp_shifted(e1, am, tab);
+                            const double l0 = exp_shifted(e0, am, ltab), l1 = exp_shifted(e1, am, ltab);
                             const double2 bb = *reinterpret_cast<const double2*>(sBe + col + 2 * t);
                             const double2 ikj = diag ? *reinterpret_cast<const double2*>(ikrow + gcol + 2 * t) : make_double2(0.0, 0.0);
                             if (sympair && gcol == row0) {

@@ -13,15 +13,15 @@ static int launch_tape_tile(const MMParams& p, cudaStream_t st) {
     if (!configured) {
         const char* e = getenv("PILCO_TAPE_VARIANT");           // tuning switch
         if (e && e[0] >= '0' && e[0] <= '3') variant = e[0] - '0';
-        const int big = (int)mm_tape_smem_bytes(TAPE_MAX_NP, 20);
+        const int big = PILCO_MAX_SMEM_OPTIN;
         if (cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 304>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
             cudaFuncSetAttribute(mm_tape_tile_kernel<KS, 352>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)
             return PILCO_ERR_LAUNCH;
         configured = true;
     }
-    if (p.L.np > TAPE_MAX_NP) return PILCO_ERR_UNSUPPORTED;
     size_t smem = mm_tape_smem_bytes(p.L.np, p.L.ldz);
+    if (p.L.np > TAPE_MAX_NP || smem > PILCO_MAX_SMEM_OPTIN) return PILCO_ERR_UNSUPPORTED;
     const dim3 grid(p.TL.cs, p.L.P, p.R);
     const bool hi = pilco_small_grid(grid);
     if (variant == 0) launch_pri(hi, mm_tape_tile_kernel<KS, 256>, grid, dim3(256), smem, st, p);

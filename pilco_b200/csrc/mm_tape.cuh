@@ -51,7 +51,7 @@ static inline __host__ __device__ MMTapeL mm_tape_layout(int n, int D, int E, in
 
 static inline __host__ __device__ size_t mm_tape_smem_bytes(int np, int ldz) {
     const int cm = np < TILE_CM ? np : TILE_CM;
-    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB * 8 + 16 + (size_t)8 * np * 8;
+    return (size_t)cm * ldz * 8 + (size_t)cm * 16 + EXP_TAB_DOUBLES * 8 + 16 + (size_t)8 * np * 8;
 }
 
 #ifdef __CUDACC__
@@ -75,6 +75,7 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
     constexpr bool ONES = (KS & 1) != 0;                       // DP = 4 KS = 4 (mod 8)
     const int g = lane >> 2, t = lane & 3;
     const int pg = (g >> 1) | ((g & 1) << 2);                  // pi(g)
+    const double* ltab = EXP_LANE_TAB(tab, lane);
     for (int cg = cbeg; cg < cend; cg += 8) {
         const double bq0 = sBq[cg + t], bq1 = sBq[cg + 4 + t];
         const double bb0 = sBe[cg + t], bb1 = sBe[cg + 4 + t];
@@ -95,7 +96,7 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
             double e0 = bq0, e1 = bq1;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) dmma884(e0, e1, ua[j][ks], bf[ks]);
-            const double l0 = exp_shifted(e0, am[j], tab), l1 = exp_shifted(e1, am[j], tab);
+            const double l0 = exp_shifted(e0, am[j], ltab), l1 = exp_shifted(e1, am[j], ltab);
             double w0, w1;
             if (DIAG) {
                 const double ik0 = ikrow[j][c0 + cg + t], ik1 = ikrow[j][c0 + cg + 4 + t];   // zero padded: in bounds
@@ -134,7 +135,7 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
     double* sBq = sZ + (size_t)CM * ldz;
     double* sBe = sBq + CM;
     double* tab = sBe + CM;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB_DOUBLES);
     double* sCs = reinterpret_cast<double*>(bar + 2);          // [8 warps][np] column-sum partials
 
     const int r = blockIdx.z, q = blockIdx.y, sidx = blockIdx.x, cs = gridDim.x;
@@ -154,11 +155,11 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
     auto issue_chunk = [&](int c0, bool with_table) {
         const int cm = (np - c0) < CM ? (np - c0) : CM;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB * 8 : 0)));
+        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB_DOUBLES * 8 : 0)));
         tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
         tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
         tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
-        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB_DOUBLES * 8), bar);
     };
     __syncthreads();                                    // barrier initialised before the first arrive / wait
     if (tid == 0) issue_chunk(0, true);
@@ -292,7 +293,8 @@ int mm_tape_backward_launch(const MMTapeBwd& bp, cudaStream_t st, bool with_redu
 // shapes the taped path supports: the tile kernel keeps 8 x np column sums, the finish tasks stage a pair's tape slice
 // -- both in shared memory (n <= 1024 centres for D <= 12, <= 704 beyond; larger models use the recomputing sweep)
 static inline __host__ __device__ bool mm_tape_supported(int n, int D) {
-    return pad64(n) <= TAPE_MAX_NP && mm_tape_bfinish_smem_bytes(pad64(n), D) + 24 * 1024 <= 220 * 1024;
+    return pad64(n) <= TAPE_MAX_NP && mm_tape_bfinish_smem_bytes(pad64(n), D) + 24 * 1024 <= 220 * 1024
+           && mm_tape_smem_bytes(pad64(n), ldz_of(D)) <= PILCO_MAX_SMEM_OPTIN;
 }
 
 #ifdef __CUDACC__

@@ -16,7 +16,8 @@ def _engine():
 
 
 @pytest.mark.parametrize("n,D,E", [(100, 3, 2), (37, 1, 1), (64, 4, 3), (130, 5, 4), (300, 12, 10),
-                                   (257, 7, 6), (65, 13, 2), (500, 10, 8), (600, 3, 2)])
+                                   (257, 7, 6), (65, 13, 2), (500, 10, 8), (600, 3, 2),
+                                   (1000, 4, 2)])        # n >= 512: multi-CTA Cholesky + DMMA GEMM path
 def test_gp_factorize_matches_oracle(n, D, E):
     from oracle import python_port as pp
     eng = _engine()

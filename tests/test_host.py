@@ -258,26 +258,31 @@ def test_plain_c_caller_links_and_runs(tmp_path):
     assert out.stdout.startswith("abi 3 mm_ws ") and "workspace" in out.stdout
 
 
-def test_table_exp_on_host(tmp_path):
-    """pilco_b200/csrc/exp_table.cuh (the 7-instruction table exp of the tile kernels, shared source) compiled for
-    the host: accuracy against libm over the range a log-kernel value can take, the row-offset form used by the
-    tile rows, and the clamp that turns padding (NEG_PAD) and far-apart centres into ~1e-304 instead of garbage."""
+@pytest.mark.parametrize("variant", ["table1024", "table256x16"])
+def test_table_exp_on_host(tmp_path, variant):
+    """pilco_b200/csrc/exp_table.cuh (the table exp of the tile kernels, shared source) compiled for the host, in both
+    table layouts (1024 entries + cubic remainder: 7 fp64 instructions; 256 entries x 16 bank-interleaved copies +
+    quartic remainder: 8): accuracy against libm over the range a log-kernel value can take, the row-offset form used
+    by the tile rows, and the clamp that turns padding (NEG_PAD) and far-apart centres into ~1e-304 instead of garbage."""
     import subprocess
     so = str(tmp_path / "exp_harness.so")
-    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++", "-o", so,
+    flags = ["-DPILCO_EXP256"] if variant == "table256x16" else []
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c++"] + flags + ["-o", so,
                            os.path.join(ROOT, "tests", "host_harness", "exp_harness.cpp")])
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)
     c = lambda a: a.ctypes.data_as(dp)
     lib.exp_harness_scale.restype = ctypes.c_double
     SC = lib.exp_harness_scale()
-    assert abs(SC - 1024.0 / np.log(2.0)) < 1e-9
-    tab = np.zeros(1024)
+    NT, STR = lib.exp_harness_entries(), lib.exp_harness_stride()
+    assert (NT, STR) == ((256, 16) if variant == "table256x16" else (1024, 1))
+    assert abs(SC - NT / np.log(2.0)) < 1e-9
+    tab = np.zeros(NT * STR)
     lib.exp_harness_table(c(tab))
-    assert tab[0] == 1.0 and abs(tab[512] - np.sqrt(2.0)) < 3e-16
+    assert tab[0] == 1.0 and abs(tab[(NT // 2) * STR] - np.sqrt(2.0)) < 3e-16
     rng = np.random.RandomState(0)
-    LD = np.longdouble                                          # x87 extended precision: reference for 2^(xs/1024)
-    ref_of = lambda xs: np.exp2(LD(xs) / LD(1024.0))
+    LD = np.longdouble                                          # x87 extended precision: reference for 2^(xs/NT)
+    ref_of = lambda xs: np.exp2(LD(xs) / LD(float(NT)))
     xs = np.concatenate([rng.uniform(-690.0, 1.0, 200000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -1.0, 1.0]]) * SC
     out = np.zeros_like(xs)
     lib.exp_harness_scaled(len(xs), c(xs), c(tab), c(out))
@@ -291,11 +296,13 @@ def test_table_exp_on_host(tmp_path):
         lib.exp_harness_shifted(len(cc), c(cc), ctypes.c_double(A), c(tab), c(o2), ctypes.byref(rf))
         tot = LD(cc) + LD(A)                                    # exact pre-scaled exponent of the element
         keep = np.asarray(tot / LD(SC) > -690.0)
-        ref2 = np.exp2(tot[keep] / LD(1024.0))
+        ref2 = np.exp2(tot[keep] / LD(float(NT)))
         assert np.abs((LD(o2[keep]) - ref2) / ref2).astype(np.float64).max() < 7e-16      # + the row-factor product and its own rounding
         assert abs(rf.value - np.exp((A - np.rint(A)) / SC)) < 2.3e-16
     # clamp: padding (NEG_PAD = -1e9 pre-scaled) and extreme negatives give a tiny positive number, never NaN/inf/negative
-    bad = np.array([-1.0e9, -5.0e6, -1.1e6, -1.0e12])
+    # (the 2^k field of exp_shifted is taken from 32 bits of the integer part: |pre-scaled exponent| < 2^(31+EXP_SHIFT),
+    #  i.e. 2^41 / 2^39 -- log-kernel values of +-1.4e9 in either layout)
+    bad = np.array([-1.0e9, -5.0e6, -1.1e6, -1.0e12 if NT == 1024 else -4.0e11])
     o3 = np.zeros_like(bad)
     rf = ctypes.c_double()
     lib.exp_harness_shifted(len(bad), c(bad), ctypes.c_double(0.0), c(tab), c(o3), ctypes.byref(rf))
