@@ -479,7 +479,7 @@ __device__ __forceinline__ void mm_breduce_body(const MMBwdParams& bp, int r) {
 // finish + reduce in ONE launch: one CTA per task; the last CTA of a restart to arrive sums the task partials (fixed
 // task order: deterministic whichever CTA that is) -- one dependent kernel less on the serial path of the reverse sweep
 template <int DP>
-__global__ void __launch_bounds__(128, 4) mm_bfinish_kernel(MMBwdParams bp) {
+__global__ void __launch_bounds__(128, 2) mm_bfinish_kernel(MMBwdParams bp) {
     PDL_ENTRY();
     const int r = blockIdx.y;
     mm_bfinish_task<DP>(bp, r, blockIdx.x);

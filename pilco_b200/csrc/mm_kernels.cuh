@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
 // visible to the CTA after __syncthreads), then all four warps sweep the centres.  One launch and one dependent
 // kernel boundary less per moment match (two per rollout step with an RBF policy).
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(128, 4) mm_setup_fused_kernel(MMParams p) {
+__global__ void __launch_bounds__(128, 2) mm_setup_fused_kernel(MMParams p) {
     PDL_ENTRY();
     const int r = blockIdx.y, task = BWD ? blockIdx.x + p.gp.E : blockIdx.x;     // BWD: ordered pair tasks only
     __shared__ double f_s[MAXD * SLD], f_L[MAXD * SLD], f_Q[MAXD * SLD], f_p[3][MAXD];

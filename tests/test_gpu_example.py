@@ -53,4 +53,12 @@ def test_compute_action_fast_path(kind):
             u = pilco.compute_action(x)
             ref = ctrl.compute_action(x, np.zeros((Ds, Ds)))[0]
             assert u.shape == (1, U) and np.max(np.abs(np.asarray(u) - np.asarray(ref))) < 1e-12
+            # ... and against the CPU oracle (numpy port of controllers.py:46-58 / 108-121), not only device vs device
+            from oracle import python_port as pp
+            maxa = np.broadcast_to(np.asarray(ctrl.max_action, dtype=np.float64).reshape(-1), (U,))[None]
+            if kind == "linear":
+                orc = pp.linear_action(np.asarray(ctrl.W), np.asarray(ctrl.b), x, np.zeros((Ds, Ds)), True, maxa)[0]
+            else:
+                orc = pp.rbf_action(np.asarray(ctrl.models[0].X), ctrl.Y, ctrl.lengthscales, x, np.zeros((Ds, Ds)), True, maxa)[0]
+            assert np.max(np.abs(np.asarray(u) - np.asarray(orc))) < 1e-9
         ctrl.randomize()                      # new parameters -> the cached plan must be rebuilt
