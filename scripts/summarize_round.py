@@ -99,6 +99,9 @@ if os.path.exists(os.path.join(src, "clocks.csv")):
             if v.lower().startswith("active"):
                 flags[nm] += 1
     with open(os.path.join(out, tag + "_clocks.txt"), "w") as f:
-        f.write("nvidia-smi -lms 200 during bench.py (metric config): %d samples, SM clock median %d MHz (min %d, max %d); reasons active: %s\n"
-                % (len(sm), sm[len(sm) // 2], sm[0], sm[-1], dict(flags) or "none"))
+        busy = [v for v in sm if v >= 0.9 * sm[-1]]
+        f.write("nvidia-smi -lms 200 over the WHOLE bench.py run (metric config; the run includes set-up and the CPU legs, during which the GPU idles at "
+                "%d MHz): %d samples, %d of them at >= 90 %% of the max clock %d MHz; throttle reasons active in any sample: %s.  "
+                "The clocks DURING the timed regions are sampled by bench.py itself (JSON key `clocks`: median under load / max / reasons).\n"
+                % (sm[0], len(sm), len(busy), sm[-1], dict(flags) or "none"))
 print("profiles/ updated for", tag)
