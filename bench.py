@@ -391,7 +391,7 @@ def run_through_api(args, cfg):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
     st = dict(policy_opt.LAST_STATS)
-    tt = torch.tensor([dt, float(st["evals"] * st["restarts_local"] * st["horizon"])], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([dt, float(st.get("rollout_steps", st["evals"] * st["restarts_local"] * st["horizon"]))], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = tt.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = tt.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
@@ -405,7 +405,7 @@ def run_through_api(args, cfg):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s; PILCO.optimize_policy(maxiter=%d, restarts=%d): lock-step L-BFGS-B, forward + reverse sweep per evaluation, wall clock incl. SciPy and host<->device copies"
                                    % (cfg["name"], args.maxiter, R * world), "restarts_per_gpu": R},
-            "loss_evaluations": st["evals"], "wall_s": dt, "best_reward": float(reward),
+            "loss_evaluations": st["evals"], "lockstep_groups": st.get("groups", 1), "wall_s": dt, "best_reward": float(reward),
         }))
     if world > 1:
         dist.destroy_process_group()
@@ -554,6 +554,77 @@ def run_ours(args, cfg):
         h_grad = torch.empty((R, 1 + gsz), dtype=torch.float64).pin_memory()
         d_grad = torch.empty((R, 1 + gsz), dtype=torch.float64, device=d)
 
+    # The restarts are independent optimisation problems: policy_opt deals them to lock-step GROUPS that only wait for
+    # their own previous evaluation, half an evaluation out of phase, so one group's latency-bound reverse sweep runs
+    # under the other's tile kernels.  The grouped arms time exactly that: K evaluations per group, back to back on the
+    # group's stream, the phase offset INSIDE the timed region.
+    G = max(1, min(args.groups, R // 8)) if args.with_backward else 1
+    gsplit3 = gsplit4 = None
+    if G > 1:
+        gb = [round(k * R / G) for k in range(G + 1)]
+        gsl = [(gb[k], gb[k + 1]) for k in range(G)]
+
+        def shifted(make, off):
+            return lambda lo, hi: make(lo + off, hi + off)
+        gsplit3 = [engine.SplitRollout(shifted(lambda lo, hi: make_plan(lo, hi, grad=True), lo), hi - lo, nsplit=nsplit_b, backward=True)
+                   for lo, hi in gsl]
+        pg5, plans5 = [dict() for _ in gsl], [dict() for _ in gsl]
+        gsplit4 = [engine.SplitRollout(shifted(plan_factory(pg5[k], plans5[k], True), lo), hi - lo, nsplit=nsplit_b, backward=True)
+                   for k, (lo, hi) in enumerate(gsl)]
+        gstreams = [torch.cuda.Stream() for _ in gsl]
+        group_ms = timeit(gsplit3[0].replay)                   # one group alone: sets the phase offset
+        stagger_ms = args.stagger_ms if args.stagger_ms > 0 else group_ms / G
+
+    def pipeline(K, e2e):
+        """K evaluations of every group; returns the elapsed device time [ms] (events on the main stream, which the
+        group streams fork from and join into)."""
+        import threading
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for st in gstreams:
+            st.wait_stream(cur)
+        if not e2e:
+            for g, st in enumerate(gstreams):
+                if g:
+                    with torch.cuda.stream(st):
+                        torch.cuda._sleep(int(g * stagger_ms * 1.9e6))     # ~SM cycles
+            for _ in range(K):
+                for g, st in enumerate(gstreams):
+                    with torch.cuda.stream(st):
+                        gsplit3[g].replay()
+        else:
+            def drive(g):
+                torch.cuda.set_device(local)
+                (lo, hi), st = gsl[g], gstreams[g]
+                time.sleep(g * stagger_ms * 1e-3)
+                with torch.cuda.stream(st):
+                    for _ in range(K):                             # what one lock-step group does per evaluation
+                        upload(plans5[g], pg5[g])
+                        rw = gsplit4[g].replay()
+                        d_grad[lo:hi, 0] = rw
+                        for (a, b), pl in plans5[g].items():
+                            d_grad[a:b, 1:] = torch.cat([pl.gbuf[k].reshape(b - a, -1) for k in gkeys], dim=1)
+                        h_grad[lo:hi].copy_(d_grad[lo:hi], non_blocking=True)
+                        st.synchronize()                           # the host optimiser needs the values
+            ths = [threading.Thread(target=drive, args=(g,)) for g in range(G)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        for st in gstreams:
+            cur.wait_stream(st)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=d)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     def step_fwd_bwd():
         split3.replay()
 
@@ -572,11 +643,16 @@ def run_ours(args, cfg):
     ms_res = timed(step_resident, args.steps, args.warmup)
     ok = int(split.info.max().item()) == 0 and bool(torch.isfinite(split.reward).all().item())
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
-    ms_fb = ms_fb_e2e = None
+    ms_fb = ms_fb_e2e = ms_fbg = ms_fbg_e2e = None
     if split3 is not None:
         kb = max(3, args.steps // 2)
         ms_fb = timed(step_fwd_bwd, kb, 3)
         ms_fb_e2e = timed(step_fwd_bwd_e2e, kb, 3)
+        if G > 1:
+            pipeline(3, False)
+            ms_fbg = pipeline(args.steps, False) / args.steps
+            pipeline(3, True)
+            ms_fbg_e2e = pipeline(args.steps, True) / args.steps
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -716,6 +792,20 @@ def run_ours(args, cfg):
               "e2e": {"value": total_steps / (ms_fb_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_fb_e2e,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(h_grad.numel()) * 8,
                       "what": "pinned host policy parameters -> device, policy factorisation, taped forward, reverse sweep, [reward | gradient] -> host"}}
+        if ms_fbg is not None:
+            # headline = the grouped pipeline (what policy_opt runs); the single lock-step batch is kept beside it
+            fb["single_group"] = {"value": fb["value"], "ms_per_step": fb["ms_per_step"], "what": fb["what"],
+                                  "e2e_value": fb["e2e"]["value"], "e2e_ms_per_step": fb["e2e"]["ms_per_step"],
+                                  "l2": "flushed between timed iterations"}
+            fb.update({"value": total_steps / (ms_fbg * 1e-3), "ms_per_step": ms_fbg, "steps": args.steps, "groups": G,
+                       "what": "taped forward cascade + tape-driven reverse sweep (policy gradient), device resident: %d lock-step groups of %d restarts "
+                               "(x %d sub-batches on parallel streams), each group's evaluations back to back on its own stream, "
+                               "groups %.1f ms out of phase (offset inside the timed region) -- the schedule policy_opt.optimize runs"
+                               % (G, R // G, nsplit_b, stagger_ms),
+                       "l2": "no flush between the pipelined steps: a step writes and re-reads its tape (%.1f GB per step over all restarts), far beyond the 126 MB L2"
+                             % (1e-9 * sum(pl.tape.numel() * 8 for sp in gsplit3 for pl in sp.plans if pl.tape is not None))})
+            fb["e2e"].update({"value": total_steps / (ms_fbg_e2e * 1e-3), "ms_per_step": ms_fbg_e2e,
+                              "what": fb["e2e"]["what"] + "; one host thread per group, stream-synchronised after every evaluation"})
         if ttile_ms:
             # taped tile pass: every pair over its full square; per element the dot, the exp, the weight and column-sum
             # updates (2 DFMA-class ops) and the second product H.[Z,1] (2 (D+1) flop)
@@ -767,6 +857,8 @@ def main():
     ap.add_argument("--no-api-line", dest="api_line", action="store_false", help="skip the PILCO.predict class-API line")
     ap.add_argument("--nsplit", type=int, default=8, help="sub-batches on parallel streams inside the captured graph (forward arms)")
     ap.add_argument("--nsplit-bwd", type=int, default=4, help="... for the forward+backward arms (measured: 4 beats 8 for the reverse sweep)")
+    ap.add_argument("--groups", type=int, default=2, help="lock-step groups of the forward+backward arms (policy_opt.GROUPS); 1 = one batch")
+    ap.add_argument("--stagger-ms", type=float, default=0.0, help="phase offset between the groups (default: one group's evaluation time / groups)")
     ap.add_argument("--through-api", action="store_true", help="drive PILCO.optimize_policy itself (lock-step L-BFGS-B, sharded restarts)")
     ap.add_argument("--maxiter", type=int, default=10, help="--through-api: L-BFGS-B iterations")
     args = ap.parse_args()

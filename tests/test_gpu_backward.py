@@ -223,6 +223,37 @@ def test_rbf_policy_optimisation_improves_reward():
     assert np.isfinite(r1) and r1 >= r0 - 1e-9
 
 
+def test_policy_optimisation_in_lockstep_groups(monkeypatch):
+    """16 restarts dealt to two lock-step groups (own evaluator, stream and driver thread each, half an evaluation out
+    of phase) must find the same per-restart optima as one lock-step batch: the restarts are independent problems
+    (pilco.py:94-108 runs them one after the other)."""
+    from pilco.models import PILCO
+    from pilco.controllers import RbfController
+    from pilco.rewards import ExponentialReward
+    from pilco_b200 import policy_opt
+    Ds, U = 3, 1
+    rng = np.random.RandomState(5)
+    X0 = rng.rand(60, Ds + U)
+    Y0 = 0.1 * np.sin(X0).dot(rng.rand(Ds + U, Ds))
+    out = {}
+    for groups in (1, 2):
+        monkeypatch.setenv("PILCO_OPT_GROUPS", str(groups))
+        np.random.seed(11)
+        ctrl = RbfController(Ds, U, 6, max_action=2.0)
+        pilco = PILCO((X0, Y0), controller=ctrl, horizon=6, reward=ExponentialReward(Ds, t=np.array([0.5, 0.5, 0.5])),
+                      m_init=X0[0:1, :Ds], S_init=0.05 * np.eye(Ds))
+        for mod in pilco.mgpr.models:
+            mod.likelihood.variance.assign(1e-3)
+            mod.kernel.lengthscales.assign(np.ones(Ds + U) * 2.0)
+        flat, best, rewards = policy_opt.optimize(pilco, maxiter=4, restarts=16)
+        assert policy_opt.LAST_STATS["groups"] == groups
+        assert policy_opt.LAST_STATS["rollout_steps"] > 0
+        out[groups] = (flat, best, np.array(rewards))
+    np.testing.assert_allclose(out[2][2], out[1][2], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out[2][1], out[1][1], rtol=1e-6)
+    np.testing.assert_allclose(out[2][0], out[1][0], rtol=1e-5, atol=1e-7)
+
+
 def test_cuda_graph_replay_matches_eager():
     """The captured H-step loop (forward + reverse sweep) must reproduce the eager results bit for bit, and keep
     doing so after the policy parameters are overwritten in place."""

@@ -355,3 +355,14 @@ def test_workspace_layouts_on_host(tmp_path):
         assert lib.layout_pair(q, ctypes.byref(a), ctypes.byref(b)) == q and 0 <= a.value <= b.value < 16
         seen.add((a.value, b.value))
     assert len(seen) == 136
+
+
+def test_lockstep_group_bounds():
+    """policy_opt deals a rank's restarts to lock-step groups of at least MIN_GROUP restarts (2 by default)."""
+    from pilco_b200.policy_opt import group_bounds
+    assert group_bounds(32) == [(0, 16), (16, 32)]
+    assert group_bounds(20) == [(0, 10), (10, 20)]
+    assert group_bounds(15) == [(0, 15)]
+    assert group_bounds(1) == [(0, 1)]
+    assert group_bounds(64, groups=4) == [(0, 16), (16, 32), (32, 48), (48, 64)]
+    assert group_bounds(17, groups=4) == [(0, 8), (8, 17)]
