@@ -745,7 +745,7 @@ def run_ours(args, cfg):
     # plain forward: symmetric (a == a) pairs need only half of their n x n elements; A'+B ride in the DMMA C operand /
     # rounding constant, so per element: the dot, one exp, one weighted add (+ trace term on diagonal pairs)
     rf = tile_block(tile_ms, (float(P) - 0.5 * E) * nn * R, 0.0, 2.0,
-                    "mm_tile_kernel<%d,3> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)" % ks,
+                    "mm_tile_kernel<%d,3,true> (dynamics GP: fp64 DMMA Q-contraction + table exp + beta/iK-weighted sums)" % ks,
                     0.5 * E * nn * R)
     # compulsory bytes per launch: iK once (shared by the batch) + per restart X-m, beta, hypers, s, outputs
     alg_bytes = 8.0 * (E * nn + R * (n_c * D + E * n_c + 2 * E * D + D * D + D + E + E * E + D * E))

@@ -11,6 +11,7 @@
 // Reference: pilco/models/mgpr.py:91-149 (gp0.m:63-104, gp2.m:69-106).
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 #define TILE_CM 512        // columns staged in shared memory per chunk
 // per-pair constants written by setup stage 1: Qa = Q diag(p_a) [MAXD*MAXD], Qb = Q diag(p_b), p_a, p_b,
@@ -768,13 +769,167 @@ __device__ __forceinline__ void mm_tile_body(const MMParams& p, int rpc) {
     TILE_STAMP(4);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Off-diagonal pairs with TWO row octets per warp (the 2 CTAs/SM instantiation): the warp takes its octet of two
+// consecutive row blocks at a time, so every column operand it reads from shared memory -- the DMMA B fragments of
+// zeta, B_q, beta_b -- feeds two tiles instead of one: 36 instead of 56 LDS per 8 tiles, and twice the independent
+// DMMA -> exp chains in flight per warp.  Measured on the instruction mix alone (scripts/ubench/fp64_mix.cu, `full16`
+// against `full`): 0.82 of the fp64 issue-path ideal at 4 warps per sub-partition against 0.77 at 6.  An odd last row
+// block runs the one-octet form of the same code.  Every group is fully unrolled (1-4 column tiles): no per-tile
+// branches anywhere.  Same staging (TMA bulk copies on one mbarrier), same per-octet outputs (Tpart) as mm_tile_body.
+// -------------------------------------------------------------------------------------------------
+template <int KS, int NR>
+__device__ __forceinline__ void tile_sweep16(const double* __restrict__ sZ, const double* __restrict__ sBq,
+                                             const double* __restrict__ sBe, const double* __restrict__ ltab, int cend,
+                                             const double (&ua)[2][KS], const double (&am)[2], double (&acc)[2], int g, int t) {
+    constexpr int ldz = KS == 1 ? 4 : (KS <= 3 ? 12 : 20);
+    int cg = 0;
+    auto group = [&](auto nt_c) {
+        constexpr int NTL = decltype(nt_c)::value;
+        double e[NR][2 * NTL];
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+            const double2 bq = *reinterpret_cast<const double2*>(sBq + cg + 8 * j + 2 * t);
+#pragma unroll
+            for (int o = 0; o < NR; ++o) { e[o][2 * j] = bq.x; e[o][2 * j + 1] = bq.y; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int j = 0; j < NTL; ++j) {
+                const double bf = sZ[(size_t)(cg + 8 * j + g) * ldz + 4 * ks + t];
+#pragma unroll
+                for (int o = 0; o < NR; ++o) dmma884(e[o][2 * j], e[o][2 * j + 1], ua[o][ks], bf);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NTL; ++j) {
+            const double2 bb = *reinterpret_cast<const double2*>(sBe + cg + 8 * j + 2 * t);
+#pragma unroll
+            for (int o = 0; o < NR; ++o) {
+                const double l0 = exp_shifted(e[o][2 * j], am[o], ltab), l1 = exp_shifted(e[o][2 * j + 1], am[o], ltab);
+                acc[o] = fma(bb.x, l0, acc[o]); acc[o] = fma(bb.y, l1, acc[o]);
+            }
+        }
+    };
+    for (; cg + 32 <= cend; cg += 32) group(std::integral_constant<int, 4>{});
+    const int ntl = (cend - cg) >> 3;                                   // 0 .. 3 tiles left (cend is a multiple of 8)
+    if (ntl == 3) group(std::integral_constant<int, 3>{});
+    else if (ntl == 2) group(std::integral_constant<int, 2>{});
+    else if (ntl == 1) group(std::integral_constant<int, 1>{});
+}
+
+template <int KS>
+__device__ __forceinline__ void mm_tile_body16(const MMParams& p, int rpc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TILE_STAMP(0);
+    const MMWs& L = p.L;
+    constexpr int ldz = KS == 1 ? 4 : (KS <= 3 ? 12 : 20);
+    const int np = L.np, n = p.gp.n;
+    const int CM = np < TILE_CM ? np : TILE_CM;
+    double* sZ = reinterpret_cast<double*>(smem_raw);
+    double* sBq = sZ + (size_t)CM * ldz;
+    double* sBe = sBq + CM;
+    double* tab = sBe + CM;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tab + EXP_TAB_DOUBLES);
+
+    const int r = blockIdx.z, q = blockIdx.y;
+    const int rb0 = blockIdx.x * rpc;
+    const int rb1 = (rb0 + rpc) < L.NB ? (rb0 + rpc) : L.NB;
+    int a, b;
+    pair_decode(q, a, b);
+    const double* wsr = p.ws + (size_t)r * L.per_r;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const double* ltab = EXP_LANE_TAB(tab, lane);
+    const int ncol8 = (n + 7) & ~7;
+    const bool single = ncol8 <= CM;
+
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    auto issue_chunk = [&](int c0, bool with_table) {
+        const int cm = (np - c0) < CM ? (np - c0) : CM;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(bar, (unsigned)(cm * ldz * 8 + cm * 16 + (with_table ? EXP_TAB_DOUBLES * 8 : 0)));
+        tma_bulk_g2s(sZ, wsr + L.zeta + (size_t)c0 * ldz, (unsigned)(cm * ldz * 8), bar);
+        tma_bulk_g2s(sBq, wsr + L.Bq + (size_t)q * np + c0, (unsigned)(cm * 8), bar);
+        tma_bulk_g2s(sBe, wsr + L.betap + (size_t)b * np + c0, (unsigned)(cm * 8), bar);
+        if (with_table) tma_bulk_g2s(tab, g_exp_tab, (unsigned)(EXP_TAB_DOUBLES * 8), bar);
+    };
+    if (tid == 0) issue_chunk(0, true);
+    TILE_STAMP(1);
+    __syncthreads();                                    // barrier initialisation visible to the waiting warps
+
+    unsigned phase = 0;
+    bool staged = true;                                 // the chunk issued at entry has not been consumed yet
+    for (int rb = rb0; rb < rb1; rb += 2) {
+        const int nr = rb + 1 < rb1 ? 2 : 1;            // row blocks of this pass (uniform over the CTA)
+        int row0[2];
+        bool act[2];
+        double ua[2][KS], am[2], ba[2], acc[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            row0[o] = (rb + o) * 64 + warp * 8;
+            act[o] = o < nr && row0[o] < n;             // warp-uniform; act[1] implies act[0]
+            am[o] = EXP_MAGIC; ba[o] = 0.0; acc[o] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) ua[o][ks] = 0.0;
+            if (o < nr) {
+                // row operands (materialised by setup stage 2): DMMA A fragments of U' and the scalar A', whose integer
+                // part rides in the rounding constant of the exp while the fractional part scales the row sums
+                const int row = row0[o] + g;
+                const double* uf = wsr + L.Ufrag + ((size_t)q * (np >> 3) + (row0[o] >> 3)) * (KS * 32);
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) ua[o][ks] = uf[ks * 32 + lane];
+                double rowfac;
+                exp_row_split(wsr[L.Arow + (size_t)q * np + row], am[o], rowfac);
+                ba[o] = wsr[L.betap + (size_t)a * np + row] * rowfac;
+            }
+        }
+        for (int c0 = 0; c0 < ncol8; c0 += CM) {
+            const int cm = (np - c0) < CM ? (np - c0) : CM;
+            const int cend = (ncol8 - c0) < cm ? (ncol8 - c0) : cm;        // chunk-local end of valid columns
+            if (staged) {                                                  // chunk issued at CTA entry
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                staged = false;
+                TILE_STAMP(2);
+            } else if (!single) {
+                __syncthreads();                                           // all warps done with the previous chunk
+                if (tid == 0) issue_chunk(c0, false);
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            }
+            if (act[1]) tile_sweep16<KS, 2>(sZ, sBq, sBe, ltab, cend, ua, am, acc, g, t);
+            else if (act[0]) tile_sweep16<KS, 1>(sZ, sBq, sBe, ltab, cend, ua, am, acc, g, t);
+        }
+        if (rb + 2 >= rb1) TILE_STAMP(3);
+        // row sums -> beta_a-weighted totals, one partial per row octet
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+            if (o < nr) {
+                double s = acc[o];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                double v = (t == 0) ? ba[o] * s : 0.0;
+                v = warp_sum(v);
+                if (lane == 0)
+                    p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * mm_tile_slots(np) + (rb + o) * 8 + warp] = act[o] ? v : 0.0;
+            }
+        }
+    }
+    TILE_STAMP(4);
+}
+
 // rpc = row blocks per CTA (launch_tile chooses it: all of them once the grid still covers the SMs)
-template <int KS, int MINB>
+template <int KS, int MINB, bool TWO = (MINB == 2)>
 __global__ void __launch_bounds__(256, MINB) mm_tile_kernel(MMParams p, int rpc) {
     PDL_ENTRY();
     int a, b;
     pair_decode(blockIdx.y, a, b);
-    if (a != b) mm_tile_body<KS, false, false>(p, rpc);
+    if (a != b) {
+        if (TWO) mm_tile_body16<KS>(p, rpc);                // two row octets per warp (the default instantiation)
+        else mm_tile_body<KS, false, false>(p, rpc);
+    }
     else if (p.gp.mode == 0 && p.gp.iK != nullptr) mm_tile_body<KS, true, true>(p, rpc);
     else mm_tile_body<KS, true, false>(p, rpc);
 }

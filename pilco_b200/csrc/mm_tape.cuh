@@ -106,18 +106,21 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
                 w0 = bb0 * l0; w1 = bb1 * l1;
             }
             if (!ONES) hl[j] += w0 + w1;
-            cs0 = fma(rf[j], w0, cs0); cs1 = fma(rf[j], w1, cs1);
+            if (!DIAG) { cs0 = fma(rf[j], w0, cs0); cs1 = fma(rf[j], w1, cs1); }
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 dmma884(hz[j][nt][0], hz[j][nt][1], w0, zb[0][nt]);
                 dmma884(hz[j][nt][0], hz[j][nt][1], w1, zb[1][nt]);
             }
         }
-        // column sums of this 8-column tile over the warp's rows: butterfly over g, lanes g == 0 own the result
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-        if (g == 0) { sCsw[c0 + cg + t] += cs0; sCsw[c0 + cg + 4 + t] += cs1; }
+        // column sums of this 8-column tile over the warp's rows: butterfly over g, lanes g == 0 own the result.
+        // Diagonal pairs of an exact GP skip them: H = G o L' is symmetric there, so hc = hr (the finish task reads hr)
+        if (!DIAG) {
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+            if (g == 0) { sCsw[c0 + cg + t] += cs0; sCsw[c0 + cg + 4 + t] += cs1; }
+        }
     }
 }
 
@@ -234,14 +237,17 @@ __device__ __forceinline__ void mm_tape_body(const MMParams& p) {
             if (lane == 0) p.ws[(size_t)r * L.per_r + L.Tpart + (size_t)q * NS + oct[j]] = v;
         }
     }
-    // column sums of this CTA's rows: fixed order over the warps (deterministic)
-    __syncthreads();
-    double* hc = tpr + TL.hc + ((size_t)q * cs + sidx) * np;
-    for (int c = tid; c < np; c += blockDim.x) {
-        double v = 0.0;
+    // column sums of this CTA's rows: fixed order over the warps (deterministic); not produced for the diagonal pairs of
+    // an exact GP (symmetric H: the finish task takes hr in their place, mm_tape_pair_is_symmetric)
+    if (!DIAG) {
+        __syncthreads();
+        double* hc = tpr + TL.hc + ((size_t)q * cs + sidx) * np;
+        for (int c = tid; c < np; c += blockDim.x) {
+            double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += sCs[(size_t)w * np + c];
-        hc[c] = v;
+            for (int w = 0; w < 8; ++w) v += sCs[(size_t)w * np + c];
+            hc[c] = v;
+        }
     }
 }
 
@@ -453,12 +459,14 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
         pair_decode(q, a, b);
         if (tid == 0) { mbar_init(&tbar, 1); mbar_fence_init(); }
         __syncthreads();
+        // diagonal pair of an exact GP: H is symmetric, the tile kernel left no column sums (hc = hr)
+        const bool symh = a == b && gp.mode == 0 && gp.iK != nullptr;
         if (tid == 0) {
-            const unsigned bhz = (unsigned)((size_t)n * TL.ldh * 8), bhr = (unsigned)(np * 8), bhc = (unsigned)((size_t)TL.cs * np * 8);
+            const unsigned bhz = (unsigned)((size_t)n * TL.ldh * 8), bhr = (unsigned)(np * 8), bhc = symh ? 0u : (unsigned)((size_t)TL.cs * np * 8);
             mbar_expect_tx(&tbar, bhz + bhr + bhc);
             tma_bulk_g2s(sHZ, tpr + TL.HZ + (size_t)q * np * TL.ldh, bhz, &tbar);
             tma_bulk_g2s(su, tpr + TL.hr + (size_t)q * np, bhr, &tbar);
-            tma_bulk_g2s(sHc, tpr + TL.hc + (size_t)q * TL.cs * np, bhc, &tbar);
+            if (!symh) tma_bulk_g2s(sHc, tpr + TL.hc + (size_t)q * TL.cs * np, bhc, &tbar);
         }
         if (tid < DP) {
             const double la = tid < D ? ell[a * D + tid] : 1.0, lb = tid < D ? ell[b * D + tid] : 1.0;
@@ -477,8 +485,10 @@ __device__ __forceinline__ void mm_tape_bfinish_task(const MMTapeBwd& bp, int r,
         // v = sum of the row splits of the column sums; rows at or beyond n carry no weight (the tile kernel never wrote them)
         for (int nn = tid; nn < np; nn += blockDim.x) {
             double v = 0.0;
-            if (nn < n) for (int k = 0; k < TL.cs; ++k) v += sHc[(size_t)k * np + nn];
-            else su[nn] = 0.0;
+            if (nn < n) {
+                if (symh) v = su[nn];
+                else for (int k = 0; k < TL.cs; ++k) v += sHc[(size_t)k * np + nn];
+            } else su[nn] = 0.0;
             sv[nn] = v;
         }
         HZg = sHZ;                                               // (shared memory from here on)

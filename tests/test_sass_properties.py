@@ -38,7 +38,7 @@ def test_device_code_targets_sm_100a():
 
 
 def test_tile_kernels_use_dmma_tma_and_no_local_memory():
-    fwd = _sass(r"mm_tile_kernelILi\dELi3E")
+    fwd = _sass(r"mm_tile_kernelILi\dELi3ELb1E")                              # the launched instantiation: 3 CTAs/SM, two row octets per warp
     bwd = _sass(r"mm_btile_kernel")
     assert len(fwd) == 4 and len(bwd) == 8                                     # KS = 1..4 (x DIAG for the backward)
     for name, text in list(fwd.items()) + list(bwd.items()):
@@ -47,20 +47,21 @@ def test_tile_kernels_use_dmma_tma_and_no_local_memory():
     for name, text in fwd.items():
         assert not re.search(r"\b(STL|LDL)\b", text), "local memory traffic in %s" % name
     metric = [t for n, t in fwd.items() if "ILi3ELi3E" in n][0]                # D = 12 instantiation (metric shape)
-    assert metric.count("DMMA.8x8x4") >= 36                                    # 12 per 4-tile group x 3 pair kinds
+    # off-diagonal body: two octets x (12 + 9 + 6 + 3) DMMA of the unrolled 4/3/2/1-tile groups + the one-octet form; diagonal bodies: 12 + 3 each
+    assert metric.count("DMMA.8x8x4") >= 60 + 30 + 30
     assert "MUFU.EX2" not in metric                                            # table exp, not the SFU path
 
 
 def test_taped_path_kernels_use_dmma_and_stay_in_registers():
     """Round 2: the taped forward tile kernel (what optimize_policy runs) and the tape-driven reverse-sweep kernel.
-    Tile: DMMA for both products (exponent + H.[Z,1]), TMA-staged columns, no local memory at any register variant,
+    Tile: DMMA for both products (exponent + H.[Z,1]), TMA-staged columns, no local memory in the launched register variant,
     table exp.  Finish: the weighted moment sums are DMMA (no DFMA inner product loops), metric-shape instantiation
     spill-free apart from a few bytes."""
     tile = _sass(r"mm_tape_tile_kernelILi\d")
     assert len(tile) == 12                                                     # KS = 1..4 x 3 register variants
     for name, text in tile.items():
         assert "DMMA.8x8x4" in text and "UBLKCP" in text and "TRYWAIT" in text, name
-        if "ELi352E" not in name or "ILi4E" not in name:                       # (the 80-register variant of D = 16 spills)
+        if "ELi256E" in name:                                                  # the launched variant (the 96- / 80-register tuning variants may spill a few scalars)
             assert not re.search(r"\b(STL|LDL)\b", text), "local memory traffic in %s" % name
         assert "MUFU.EX2" not in text, name
     metric = [t for n, t in tile.items() if "ILi3ELi256E" in n][0]             # D = 12, default register variant
