@@ -425,9 +425,9 @@ __device__ __forceinline__ void mm_setup2_task(const MMParams& p, int r, int tas
                 const int i0 = 8 * nt + 2 * t;                  // this lane's two columns of the C fragment
                 if (i0 < DP) qbp = fma(pb[i0] * zr[i0], vb[nt][0], fma(pb[i0 + 1] * zr[i0 + 1], vb[nt][1], qbp));
             }
-            kbp += __shfl_xor_sync(0xffffffffu, kbp, 1); kbp += __shfl_xor_sync(0xffffffffu, kbp, 2);
-            qbp += __shfl_xor_sync(0xffffffffu, qbp, 1); qbp += __shfl_xor_sync(0xffffffffu, qbp, 2);
-            if (t == 0) wsr[L.Bq + (size_t)q * np + row] = row < n ? EXP_SC * (lsb - 0.5 * kbp + qbp) : NEG_PAD;
+            double xb = fma(-0.5, kbp, qbp);                     // one quad reduction for both terms
+            xb += __shfl_xor_sync(0xffffffffu, xb, 1); xb += __shfl_xor_sync(0xffffffffu, xb, 2);
+            if (t == 0) wsr[L.Bq + (size_t)q * np + row] = row < n ? EXP_SC * (lsb + xb) : NEG_PAD;
             if (!BWD) {
                 // row side of the same 8 centres: DMMA A fragments of U' and the scalar A' (see tile_row_operands),
                 // written in the layout the tile kernel's prologue loads with three coalesced 8-byte loads per lane
@@ -466,32 +466,39 @@ __global__ void __launch_bounds__(128, 2) mm_setup_fused_kernel(MMParams p) {
 
 // Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
 // U' = 2 EXP_SC p_b o (Qa zeta_row), and the scalar A'[row] = EXP_SC (log sf2_a - 0.5 sum p_a zeta^2 + z_a'Q z_a
-// - 0.5 log det R).  2*ceil(DP/8)*KS DMMA + 2 KS shuffles per 8 rows.  The pair constants (this lane's B fragments
+// - 0.5 log det R).  2*ceil(DP/8)*KS DMMA + ONE quad reduction per 8 rows (no layout shuffles: permuted B fragments).  The pair constants (this lane's B fragments
 // of Qa and its slices of p_a, p_b) are loaded once (RowOpConsts) and reused for every row octet.
 template <int KS>
 struct RowOpConsts {
     static constexpr int DP = 4 * KS, NT = (DP + 7) / 8;
-    double bq[KS][NT];          // B fragments: Qa[8 nt + g][4 ks + t]
+    // B fragments of Qa with PERMUTED columns: column c of n-tile nt is Qa row 8 nt + pi(c), pi = (0,4,1,5,2,6,3,7), so
+    // that the C fragment of Z.Qa' (row g; this lane's two columns = actual columns 8 nt + t and 8 nt + 4 + t) IS the
+    // A-fragment layout of k-steps 2 nt and 2 nt + 1 -- U' leaves the product without a single shuffle (the same
+    // trick as the taped tile kernel's second product)
+    double bq[KS][NT];
     double pak[KS];             // p_a[4 ks + t]
-    double pac[NT][2], pbc[NT][2];   // p_a, p_b at this lane's C-fragment columns 8 nt + 2 t (+1)
+    double pac[NT][2], pbc[NT][2];   // p_a, p_b at this lane's C-fragment columns 8 nt + t, 8 nt + 4 + t
     double lsa, hld;            // log sf2_a, 0.5 log det R
     __device__ __forceinline__ void load(const double* __restrict__ blk, int lane) {
         const int g = lane >> 2, t = lane & 3;
+        const int pg = (g >> 1) | ((g & 1) << 2);              // pi(g)
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             pak[ks] = blk[PAIR_PA + 4 * ks + t];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const int i = 8 * nt + g;
+                const int i = 8 * nt + pg;
                 bq[ks][nt] = i < DP ? blk[PAIR_QA + i * DP + 4 * ks + t] : 0.0;
             }
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            const int i0 = 8 * nt + 2 * t;
-            const bool in = i0 < DP;
-            pac[nt][0] = in ? blk[PAIR_PA + i0] : 0.0; pac[nt][1] = in ? blk[PAIR_PA + i0 + 1] : 0.0;
-            pbc[nt][0] = in ? blk[PAIR_PB + i0] : 0.0; pbc[nt][1] = in ? blk[PAIR_PB + i0 + 1] : 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = 8 * nt + 4 * h + t;
+                pac[nt][h] = c < DP ? blk[PAIR_PA + c] : 0.0;
+                pbc[nt][h] = c < DP ? blk[PAIR_PB + c] : 0.0;
+            }
         }
         lsa = blk[PAIR_SC + 1]; hld = blk[PAIR_SC + 0];
     }
@@ -504,11 +511,11 @@ __device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, c
     constexpr int DP = 4 * KS, NT = (DP + 7) / 8;
     const int t = lane & 3;
     double z[KS], va[NT][2];
-    double kap = 0.0;
+    double x = 0.0;                                             // this lane's share of z_a'Q z_a - 0.5 sum p_a zeta^2
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         z[ks] = zr[4 * ks + t];
-        kap = fma(c.pak[ks] * z[ks], z[ks], kap);
+        x = fma(-0.5 * c.pak[ks] * z[ks], z[ks], x);
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { va[nt][0] = va[nt][1] = 0.0; }
@@ -516,30 +523,15 @@ __device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, c
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) dmma884(va[nt][0], va[nt][1], z[ks], c.bq[ks][nt]);
-    double qap = 0.0;
-    double uc[NT][2];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const int i0 = 8 * nt + 2 * t;
-        uc[nt][0] = uc[nt][1] = 0.0;
-        if (i0 < DP) {
-            qap = fma(c.pac[nt][0] * zr[i0], va[nt][0], fma(c.pac[nt][1] * zr[i0 + 1], va[nt][1], qap));
-            uc[nt][0] = (2.0 * EXP_SC) * c.pbc[nt][0] * va[nt][0];
-            uc[nt][1] = (2.0 * EXP_SC) * c.pbc[nt][1] * va[nt][1];
-        }
-    }
-    kap += __shfl_xor_sync(0xffffffffu, kap, 1); kap += __shfl_xor_sync(0xffffffffu, kap, 2);
-    qap += __shfl_xor_sync(0xffffffffu, qap, 1); qap += __shfl_xor_sync(0xffffffffu, qap, 2);
-    Apv = live ? EXP_SC * (c.lsa - 0.5 * kap + qap - c.hld) : NEG_PAD;
-    // C-fragment layout (row g, cols 8nt+2t,+1) -> A-fragment layout (row g, col 4ks+t)
+    // va[nt][h] = (Qa zeta)[8 nt + 4 h + t] of row g: column 4 ks + t with ks = 2 nt + h, i.e. A-fragment layout already
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        const int nt = ks >> 1;                                 // col 4ks+t lies in n-tile ks/2 ...
-        const int src = (lane & ~3) | (((ks & 1) << 1) | (t >> 1));   // ... held by quad lane (4(ks&1)+t)/2
-        const double x0 = __shfl_sync(0xffffffffu, uc[nt][0], src);
-        const double x1 = __shfl_sync(0xffffffffu, uc[nt][1], src);
-        ua[ks] = (t & 1) ? x1 : x0;
+        const int nt = ks >> 1, h = ks & 1;
+        x = fma(c.pac[nt][h] * z[ks], va[nt][h], x);            // (zeta at that column is this lane's z[ks])
+        ua[ks] = (2.0 * EXP_SC) * c.pbc[nt][h] * va[nt][h];
     }
+    x += __shfl_xor_sync(0xffffffffu, x, 1); x += __shfl_xor_sync(0xffffffffu, x, 2);       // one quad reduction for both terms
+    Apv = live ? EXP_SC * (c.lsa + x - c.hld) : NEG_PAD;
 }
 
 // one-shot form (backward tile kernel prologue): zeta rows are read from the workspace (L2 resident)

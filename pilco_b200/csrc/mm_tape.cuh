@@ -116,10 +116,16 @@ __device__ __forceinline__ void tape_sweep(const double* __restrict__ sZ, const 
         // column sums of this 8-column tile over the warp's rows: butterfly over g, lanes g == 0 own the result.
         // Diagonal pairs of an exact GP skip them: H = G o L' is symmetric there, so hc = hr (the finish task reads hr)
         if (!DIAG) {
-            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 4);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 4);
-            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-            if (g == 0) { sCsw[c0 + cg + t] += cs0; sCsw[c0 + cg + 4 + t] += cs1; }
+            // reduce-scatter: the first exchange (rows g <-> g ^ 4) hands each lane the partner's partial of ONE of its two
+            // columns (g < 4 keeps column t, g >= 4 keeps column 4 + t), so the remaining two levels move one value, not
+            // two: 3 instead of 6 64-bit shuffles per tile (the shuffles, not the adds, are what this costs)
+            const bool up = (g & 4) != 0;
+            double keep = up ? cs1 : cs0;
+            const double send = up ? cs0 : cs1;
+            keep += __shfl_xor_sync(0xffffffffu, send, 16);
+            keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+            keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+            if ((g & 3) == 0) sCsw[c0 + cg + (up ? 4 : 0) + t] += keep;
         }
     }
 }
