@@ -821,7 +821,7 @@ def run_ours(args, cfg):
         if fb is not None:
             vb, sb = cr.steps_per_s(reps=1, h=2 if n_c >= 200 else min(H, 6), grad=True, budget_s=20.0)
             fb["cpu_baseline"] = {"value": vb, "unit": UNIT, "cores": cr.threads, "kind": "port", "sample": sb}
-    launches_per_rollout = (H * (8 if bf else 4) + 1) + 1      # per sub-batch: ro_state + [policy: setup1, setup2, tile, ro_policy] + dyn (setup1, setup2, tile); + memset
+    launches_per_rollout = (H * (8 if bf else 4) + 1) + 1 + 2  # per sub-batch: ro_state + [policy: setup1, setup2, tile, ro_policy] + dyn (setup1, setup2, tile); + memset; + ro_reward, ro_reward_sum
     line = {
         "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

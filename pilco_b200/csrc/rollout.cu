@@ -3,10 +3,13 @@
 //
 // Launch sequence per step t (all on one stream, graph-capturable, no host sync):
 //   ro_state<t>   grid R : [t>0: finish dynamics MM of step t-1 + next-state glue] -> traj[t];
-//                          reward(traj[t]); linear policy + squash + joint Gaussian
+//                          linear policy + squash + joint Gaussian
 //   (RBF policy)  mm_setup/mm_tile on the policy GP, then ro_policy<t>: finish + squash + joint
 //   mm_setup / mm_tile on the dynamics GP with the joint Gaussian of step t
-// and a final ro_state<H> that closes the last step.
+// and a final ro_state<H> that closes the last step.  The expected rewards depend on the trajectory only, so they are
+// NOT on this chain (an LU factorisation per step and restart would sit on the serial path of every step): one
+// ro_reward launch over all (t, r) after the last step, then ro_reward_sum adds them in step order (same summation
+// order, hence the same bits, as a running sum).
 #include "rollout.cuh"
 #include "mm_tape.cuh"
 #include "small_kernels.cuh"
@@ -20,6 +23,7 @@ struct RoDev {
     const double* m0; long long m0_bs; const double* S0; long long S0_bs;
     double* traj_m; double* traj_S; double* reward; double* step_reward;
     double* risk; double* step_risk; double mult_mu; int n_mult;     // MULT channel (SafePILCO): risk[t*R + r]
+    double* rew;                                                      // additive channel per step: rew[t*R + r]
     // per-step slots [R, len] for step t (cur) and t-1 (prev)
     double *mj, *sj, *Mp, *Sp, *Vp, *Mu, *Su, *Cq, *Vu;
     double *mj_prev, *sj_prev, *Md_prev, *Sd_prev, *Vd_prev;
@@ -62,7 +66,6 @@ __global__ void __launch_bounds__(128) ro_state_kernel(RoDev p) {
     if (t == 0) {
         for (int i = tid; i < Ds; i += nt) mx[i] = p.m0[(size_t)r * p.m0_bs + i];
         for (int e = tid; e < Ds * Ds; e += nt) sx[e] = p.S0[(size_t)r * p.S0_bs + e];
-        if (tid == 0) p.reward[r] = 0.0;
         __syncthreads();
     } else {
         mm_finish_device(p.dyn_prev, r);
@@ -73,31 +76,7 @@ __global__ void __launch_bounds__(128) ro_state_kernel(RoDev p) {
                  p.Md_prev + (size_t)r * Ds, p.Sd_prev + (size_t)r * Ds * Ds, p.Vd_prev + (size_t)r * D * Ds,
                  mx, sx, sc);
     }
-    if (t >= p.H) {
-        // SafePILCO.predict (safe_pilco.py:49): reward_add + mu (1 - prod_t (1 - risk_t))
-        if (p.n_mult > 0 && tid == 0) {
-            double mult = 1.0;
-            for (int tt = 0; tt < p.H; ++tt) mult *= 1.0 - p.risk[(size_t)tt * p.R + r];
-            p.reward[r] += p.mult_mu * (1.0 - mult);
-        }
-        return;
-    }
-    // expected reward at the pre-step state (pilco.py:130-134)
-    double rew = 0.0, risk = 0.0;
-    for (int k = 0; k < p.n_rewards; ++k) {
-        const pilco_reward_term& rt = p.rewards[k];
-        const double mu = dev_reward_value(Ds, rt, mx, sx, sc);
-        if (rt.channel == PILCO_CHANNEL_MULT) risk = fma(rt.coef, mu, risk);
-        else rew = fma(rt.coef, mu, rew);
-    }
-    if (tid == 0) {
-        p.reward[r] += rew;
-        if (p.step_reward) p.step_reward[(size_t)r * p.H + t] = rew;
-        if (p.n_mult > 0) {
-            p.risk[(size_t)t * p.R + r] = risk;
-            if (p.step_risk) p.step_risk[(size_t)r * p.H + t] = risk;
-        }
-    }
+    if (t >= p.H) return;
     if (p.pol_kind == PILCO_POLICY_LINEAR) {
         dev_linear_action(Ds, U, p.W + (size_t)r * p.W_bs, p.b + (size_t)r * p.b_bs, mx, sx,
                           p.Mp + (size_t)r * U, p.Sp + (size_t)r * U * U, p.Vp + (size_t)r * Ds * U, sc);
@@ -114,6 +93,45 @@ __global__ void __launch_bounds__(128) ro_policy_kernel(RoDev p) {
     const double* mx = p.traj_m + ((size_t)r * (p.H + 1) + t) * Ds;
     const double* sx = p.traj_S + ((size_t)r * (p.H + 1) + t) * Ds * Ds;
     ro_action_tail(p, r, mx, sx, sc);
+}
+
+// expected reward at the pre-step state of every step (pilco.py:130-134), CTA = (step t, restart r)
+__global__ void __launch_bounds__(128) ro_reward_kernel(RoDev p) {
+    PDL_ENTRY();
+    __shared__ SmallScratch sc;
+    const int t = blockIdx.x, r = blockIdx.y, Ds = p.Ds;
+    const double* mx = p.traj_m + ((size_t)r * (p.H + 1) + t) * Ds;
+    const double* sx = p.traj_S + ((size_t)r * (p.H + 1) + t) * Ds * Ds;
+    double rew = 0.0, risk = 0.0;
+    for (int k = 0; k < p.n_rewards; ++k) {
+        const pilco_reward_term& rt = p.rewards[k];
+        const double mu = dev_reward_value(Ds, rt, mx, sx, sc);
+        if (rt.channel == PILCO_CHANNEL_MULT) risk = fma(rt.coef, mu, risk);
+        else rew = fma(rt.coef, mu, rew);
+    }
+    if (threadIdx.x == 0) {
+        p.rew[(size_t)t * p.R + r] = rew;
+        if (p.step_reward) p.step_reward[(size_t)r * p.H + t] = rew;
+        if (p.n_mult > 0) {
+            p.risk[(size_t)t * p.R + r] = risk;
+            if (p.step_risk) p.step_risk[(size_t)r * p.H + t] = risk;
+        }
+    }
+}
+
+// reward[r] = sum_t rew[t, r] in step order  (+ SafePILCO.predict, safe_pilco.py:49: mu (1 - prod_t (1 - risk_t)))
+__global__ void __launch_bounds__(128) ro_reward_sum_kernel(RoDev p) {
+    PDL_ENTRY();
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    double s = 0.0;
+    for (int tt = 0; tt < p.H; ++tt) s += p.rew[(size_t)tt * p.R + r];
+    if (p.n_mult > 0) {
+        double mult = 1.0;
+        for (int tt = 0; tt < p.H; ++tt) mult *= 1.0 - p.risk[(size_t)tt * p.R + r];
+        s += p.mult_mu * (1.0 - mult);
+    }
+    p.reward[r] = s;
 }
 
 int ro_check(const pilco_rollout* ro) {
@@ -180,7 +198,7 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
     for (int k = 0; k < 8; ++k) d.rewards[k] = ro->rewards[k];
     d.m0 = ro->m0; d.m0_bs = ro->m0_bs; d.S0 = ro->S0; d.S0_bs = ro->S0_bs;
     d.traj_m = ro->traj_m; d.traj_S = ro->traj_S; d.reward = ro->reward; d.step_reward = ro->step_reward;
-    d.risk = ws + L.risk; d.step_risk = ro->step_risk; d.mult_mu = ro->mult_mu; d.n_mult = ro_count_mult(ro);
+    d.risk = ws + L.risk; d.rew = ws + L.rew; d.step_risk = ro->step_risk; d.mult_mu = ro->mult_mu; d.n_mult = ro_count_mult(ro);
 
     auto slot = [&](size_t base, size_t len, int t) { return ws + base + (size_t)t * RR * len; };
     auto dyn_params = [&](int t) {
@@ -235,6 +253,12 @@ int pilco_rollout_forward(const pilco_rollout* ro, pilco_stream_t stream) {
         rc = mm_forward_launch(dyn_params(t), st, false);
         if (rc) return rc;
     }
+    if (H > 0) {
+        launch_hi(ro_reward_kernel, dim3(H, R), dim3(128), 0, st, d);
+        CUDA_LAUNCH_CHECK();
+    }
+    launch_hi(ro_reward_sum_kernel, dim3((R + 127) / 128), dim3(128), 0, st, d);
+    CUDA_LAUNCH_CHECK();
     return PILCO_OK;
 }
 

@@ -3,7 +3,7 @@
 #include "mm_kernels.cuh"
 
 struct RoWs {                 // offsets in doubles
-    size_t mj, sj, Md, Sd, Vd, Mp, Sp, Vp, Mu, Su, Cq, Vu, risk, dynws, polws, total;
+    size_t mj, sj, Md, Sd, Vd, Mp, Sp, Vp, Mu, Su, Cq, Vu, risk, rew, dynws, polws, total;
 };
 
 static inline RoWs ro_ws_layout(const pilco_rollout* ro) {
@@ -16,6 +16,7 @@ static inline RoWs ro_ws_layout(const pilco_rollout* ro) {
     L.Mp = take(U); L.Sp = take(U * U); L.Vp = take(Ds * U);
     L.Mu = take(U); L.Su = take(U * U); L.Cq = take(U * U); L.Vu = take(Ds * U);
     L.risk = take(1);                       // per-step risk of the MULT reward channel, [H][R]
+    L.rew = take(1);                        // per-step additive reward, [H][R] (summed in step order by ro_reward_sum_kernel)
     L.dynws = o; o += pilco_mm_workspace_bytes(ro->dyn.n, ro->dyn.D, ro->dyn.E, ro->R) / 8;
     L.polws = o;
     if (ro->pol.kind == PILCO_POLICY_RBF)
