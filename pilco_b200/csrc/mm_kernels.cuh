@@ -277,7 +277,7 @@ __device__ __forceinline__ void row_operands_compute(const RowOpConsts<KS>& c, c
 
 // stage 2: the throughput part: one CTA (128 threads) per task sweeps the centres
 template <int DP, bool BWD>
-__device__ __forceinline__ void mm_setup2_task(const MMParams& p, int r, int task) {
+__device__ __forceinline__ void mm_setup2_task(const MMParams& p, int r, int task, int part = 0, int nparts = 1) {
     const pilco_gp_model& gp = p.gp;
     const int n = gp.n, D = gp.D, E = gp.E;
     const MMWs& L = p.L;
@@ -385,7 +385,8 @@ __device__ __forceinline__ void mm_setup2_task(const MMParams& p, int r, int tas
     const double lsb = blk[PAIR_SC + 2];
     RowOpConsts<KS> roc;                                        // row-side pair constants, loaded once per CTA
     if (!BWD) roc.load(blk, lane);
-    for (int n0 = 0; n0 < np; n0 += 128) {
+    // (pair tasks may be split over `nparts` CTAs in the latency regime: CTA `part` takes every nparts-th 128-row chunk)
+    for (int n0 = 128 * part; n0 < np; n0 += 128 * nparts) {
         // stage zeta[n0 : n0+128, 0:ldz] = X - m (zero outside [n, D)) in shared memory, coalesced
         __syncthreads();
         for (int e = tid; e < 128 * ldz; e += blockDim.x) {
@@ -453,15 +454,23 @@ __global__ void __launch_bounds__(128) mm_setup2_kernel(MMParams p) {
 // visible to the CTA after __syncthreads), then all four warps sweep the centres.  One launch and one dependent
 // kernel boundary less per moment match (two per rollout step with an RBF policy).
 template <int DP, bool BWD>
-__global__ void __launch_bounds__(128, 2) mm_setup_fused_kernel(MMParams p) {
+__global__ void __launch_bounds__(128, 2) mm_setup_fused_kernel(MMParams p, int split) {
     PDL_ENTRY();
-    const int r = blockIdx.y, task = BWD ? blockIdx.x + p.gp.E : blockIdx.x;     // BWD: ordered pair tasks only
+    // `split` CTAs share a pair task: each repeats the (short, serial) stage 1 -- they write identical pair blocks --
+    // and sweeps every split-th 128-row chunk in stage 2, whose latency is what the single-restart step waits for
+    const int r = blockIdx.y, E = p.gp.E;
+    int task, part = 0, nparts = 1;
+    if (!BWD && (int)blockIdx.x < E) task = blockIdx.x;                           // output task: one CTA (it reduces over all centres)
+    else {
+        const int k = BWD ? (int)blockIdx.x : (int)blockIdx.x - E;               // BWD: ordered pair tasks only
+        task = E + k / split; part = k % split; nparts = split;
+    }
     __shared__ double f_s[MAXD * SLD], f_L[MAXD * SLD], f_Q[MAXD * SLD], f_p[3][MAXD];
     setup_stage_s<DP>(p, r, f_s);
     __syncthreads();
     if (threadIdx.x < 32) mm_setup1_task<DP, BWD>(p, r, task, threadIdx.x, f_s, f_L, f_Q, f_p[0], f_p[1], f_p[2]);
     __syncthreads();
-    mm_setup2_task<DP, BWD>(p, r, task);
+    mm_setup2_task<DP, BWD>(p, r, task, part, nparts);
 }
 
 // Row-side operands of one warp's 8 rows for the pair block `blk`: DMMA A fragments ua[ks] = U'[row][4ks+t] with
@@ -556,7 +565,10 @@ static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
         if (mode < 0) { const char* e = getenv("PILCO_SETUP_FUSED"); mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }
         const bool fused = mode == 2 ? (long long)ntask * p.R <= 160 : mode == 1;
         if (fused) {
-            launch_hi(mm_setup_fused_kernel<DP, BWD>, dim3(ntask, p.R), dim3(128), 0, st, p);
+            int split = (p.L.np + 127) / 128;                    // one 128-row chunk per CTA, at most 3 CTAs per pair task
+            if (split > 3) split = 3;
+            const int npair = p.L.P;                              // (BWD: P counts the ordered pairs)
+            launch_hi(mm_setup_fused_kernel<DP, BWD>, dim3((ntask - npair) + npair * split, p.R), dim3(128), 0, st, p, split);
             return;
         }
     }
