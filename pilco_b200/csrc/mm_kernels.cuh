@@ -557,15 +557,19 @@ __device__ __forceinline__ void tile_row_operands(const double* __restrict__ blk
 template <int DP, bool BWD>
 static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
     const int ntask = BWD ? p.L.P : p.gp.E + p.L.P;
-    // ONE launch while the batch is small (latency regime: every launch on the serial path of a rollout
-    // step counts); big batches keep the two-stage form (stage 1 is register-hungry: fused, it caps the occupancy of the
-    // throughput stage).  PILCO_SETUP_FUSED=0/1 forces either (tuning switch).
+    // ONE launch while the whole launch is small -- at most half the SMs' worth of CTAs: a single restart, or the RBF
+    // policy's few tasks -- (latency regime: every launch on the serial path of a rollout step counts); anything bigger keeps
+    // the two-stage form: stage 1 is register-hungry (218 registers at D = 12), fused it caps the occupancy of the throughput
+    // stage, and in a sub-batch of a larger job its CTAs take SM slots from the other sub-batches' tile kernels (measured,
+    // inv_double_pendulum R = 32 in 8 sub-batches of 27 tasks x 4: fused 194 k, two-stage 206 k steps/s).
+    // PILCO_SETUP_FUSED=0/1 forces either (tuning switch).
     {
         static int mode = -1;
         if (mode < 0) { const char* e = getenv("PILCO_SETUP_FUSED"); mode = (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }
-        const bool fused = mode == 2 ? (long long)ntask * p.R <= 160 : mode == 1;
+        const bool fused = mode == 2 ? (long long)ntask * p.R <= 74 : mode == 1;
         if (fused) {
-            int split = (p.L.np + 127) / 128;                    // one 128-row chunk per CTA, at most 3 CTAs per pair task
+            // pair tasks are split over up to 3 CTAs, one 128-row chunk each (the stage-2 sweep is what the step waits for)
+            int split = (p.L.np + 127) / 128;
             if (split > 3) split = 3;
             const int npair = p.L.P;                              // (BWD: P counts the ordered pairs)
             launch_hi(mm_setup_fused_kernel<DP, BWD>, dim3((ntask - npair) + npair * split, p.R), dim3(128), 0, st, p, split);
