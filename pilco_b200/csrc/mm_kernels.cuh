@@ -581,9 +581,10 @@ static inline void mm_setup_launch(const MMParams& p, cudaStream_t st) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// tile kernel: CTA = (row block of 64 centres, pair, restart), 8 warps x 8 rows.  The column operands
-// (zeta [cols, ldz], B_q, beta_b) are staged in shared memory by TMA bulk copies; each warp sweeps all
-// (valid) columns in groups of 4 DMMA tiles.  Diagonal pairs (a == b) exploit the symmetry of
+// tile kernel: CTA = (row blocks of 64 centres, pair, restart), 8 warps; a warp owns one row octet of each row block.
+// The column operands (zeta [cols, ldz], B_q, beta_b) are staged in shared memory by TMA bulk copies; each warp
+// sweeps all (valid) columns in groups of 4 DMMA tiles.  Off-diagonal pairs run mm_tile_body16 (two row blocks, i.e.
+// 16 rows per warp, at a time -- below); diagonal pairs (a == b) run mm_tile_body and exploit the symmetry of
 // G[n,m] L'[n,m]: only column tiles at or right of the row tile are visited, strictly-upper tiles count twice.
 // -------------------------------------------------------------------------------------------------
 static inline __host__ __device__ size_t mm_tile_smem_bytes(int np, int ldz) {

@@ -81,3 +81,20 @@ def test_reverse_sweep_policy_kernels_present():
     assert sum("mm_bfinish_kernel" in n for n in names) == 4
     assert not any("mm_breduce_kernel" in n for n in names)
     assert sum("mm_setup_fused_kernel" in n for n in names) == 8               # DP = 4..16 x {forward, ordered-pair backward}
+
+
+def test_session3_shuffle_and_chain_properties():
+    """Round 2, session 3: (1) the taped tile kernel's column sums use a reduce-scatter butterfly (3 64-bit shuffles per
+    tile, none for the symmetric diagonal pairs): the whole metric-shape kernel -- four sweep loops plus the per-pass warp
+    reductions -- holds fewer than 100 SHFL (it was 152 with the 6-shuffle butterfly in every loop); (2) the expected rewards
+    are their own kernels, off the per-step chain: ro_state carries no LU / reward code any more (two shuffles: the
+    partial-sum pairs of mm_finish)."""
+    tile = _sass(r"mm_tape_tile_kernelILi3ELi256E")
+    assert len(tile) == 1
+    assert sum(t.count("SHFL") for t in tile.values()) < 100
+    ro = _sass(r"ro_state_kernel|ro_reward_kernel|ro_reward_sum_kernel")
+    assert len(ro) == 3
+    state = [t for n, t in ro.items() if "ro_state" in n][0]
+    assert state.count("SHFL") <= 4
+    rew = [t for n, t in ro.items() if "ro_reward_kernel" in n][0]
+    assert "MUFU" in rew                                                          # the reward's divisions / sqrt live here now
