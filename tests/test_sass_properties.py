@@ -86,7 +86,7 @@ def test_reverse_sweep_policy_kernels_present():
 def test_session3_shuffle_and_chain_properties():
     """Round 2, session 3: (1) the taped tile kernel's column sums use a reduce-scatter butterfly (3 64-bit shuffles per
     tile, none for the symmetric diagonal pairs): the whole metric-shape kernel -- four sweep loops plus the per-pass warp
-    reductions -- holds fewer than 100 SHFL (it was 152 with the 6-shuffle butterfly in every loop); (2) the expected rewards
+    reductions -- holds fewer than 100 SHFL (it was 128 with the 6-shuffle butterfly in every loop); (2) the expected rewards
     are their own kernels, off the per-step chain: ro_state carries no LU / reward code any more (two shuffles: the
     partial-sum pairs of mm_finish)."""
     tile = _sass(r"mm_tape_tile_kernelILi3ELi256E")
