@@ -98,3 +98,29 @@ def test_session3_shuffle_and_chain_properties():
     assert state.count("SHFL") <= 4
     rew = [t for n, t in ro.items() if "ro_reward_kernel" in n][0]
     assert "MUFU" in rew                                                          # the reward's divisions / sqrt live here now
+
+
+def test_issue_model_of_the_hot_loops():
+    """scripts/issue_model.py on the built library: the structure of the innermost DMMA loops DESIGN.md section 6 reasons about.
+    Forward tile kernel (metric shape): the two-octet loop issues 24 DMMA per 8 tiles with 36 LDS (one octet: 12 per 4 tiles,
+    28 LDS) and not one shuffle; priced with the measured rates (DMMA 16 cycles, fp64 2, three-register DFMA 3) that is
+    82 cycles per 8x8 tile.  Taped tile kernel: 14 DMMA per tile and octet pair; 6 shuffles in the loops of the non-symmetric
+    pairs, none in those of the symmetric diagonal pairs."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import issue_model
+    fwd = list(issue_model.analyse(r"mm_tile_kernelILi3ELi3ELb1E").values())
+    assert len(fwd) == 1
+    two = [c for _, c in fwd[0] if c["dmma"] == 24]
+    one = [c for _, c in fwd[0] if c["dmma"] == 12]
+    assert len(two) == 1 and len(one) == 1
+    assert two[0]["shfl"] == 0 and one[0]["shfl"] == 0
+    assert two[0]["lds"] <= 36 and one[0]["lds"] <= 28
+    assert two[0]["cycles"] == 2 * one[0]["cycles"] and 80 <= two[0]["cycles"] / 8.0 <= 84      # 12*16 + 8*(7*2+3) = 328 per 4 tiles
+    tape = list(issue_model.analyse(r"mm_tape_tile_kernelILi3ELi256E").values())
+    assert len(tape) == 1
+    pair_loops = [c for _, c in tape[0] if c["dmma"] == 14]
+    single_loops = [c for _, c in tape[0] if c["dmma"] == 7]
+    assert len(pair_loops) == 2 and len(single_loops) == 2                         # {symmetric diagonal, other} pairs x {2, 1} live octets
+    assert sorted(c["shfl"] for c in pair_loops) == [0, 6]
+    assert sorted(c["shfl"] for c in single_loops) == [0, 6]
